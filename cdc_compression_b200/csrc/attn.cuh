@@ -1,0 +1,374 @@
+// Linear attention (heads=1, dim_head=C) with the PreNorm LayerNorm folded into GEMM epilogues.
+// Reference: epsilonparam/modules/network_components.py:117-139 (+PreNorm :69-77, Residual :10-16).
+//
+//   K,V = rstd*(Wg x - mean*u) + c            (Wg = W diag(g_ln) in fp16, u = rowsum(Wg), c = W b_ln)
+//   P   = exp(K - max_n K)  (softmax over pixels, per channel d);  S_d = sum_n P
+//   ctx[d,e] = sum_n P[n,d] V[n,e] / S_d
+//   out = M_b xn + b_out + x,  M_b = W_out ctx^T (C^-1/2 W_q)      
+//
+// attn_ctx_kernel   : one pass over x per (image, pixel chunk, 64x64 block of ctx): K/V GEMM,
+//                     online softmax over pixels, P^T V accumulation; writes split partials.
+// attn_combine_kernel, sgemm_tn_kernel, attn_finish_kernel : per-image C x C algebra (fp32).
+// The final GEMM (out = M_b-folded weights applied to raw x) runs in the generic conv kernel
+// with EPI_AFFINE and per-image weights.
+#pragma once
+#include "common.cuh"
+
+namespace cdc {
+
+struct AttnCtxParams {
+  const __half* x;      // [B, N, C] fp16 (NHWC)
+  const float2* stats;  // [B*N] (mean, rstd) of x rows
+  const __half* Wkv;    // [C/64][2C][64] fp16, LayerNorm gain folded in; rows [0,C) = K, [C,2C) = V
+  const float* u;       // [2C] row sums of the folded fp16 weights
+  const float* c;       // [2C] W b_ln
+  int C, N;
+  int tiles_per_chunk;  // 64-pixel tiles walked by one CTA
+  int nchunks;
+  float* part_ctx;      // [B][nchunks][C][C]
+  float* part_m;        // [B][nchunks][C]
+  float* part_s;        // [B][nchunks][C]
+};
+
+struct AttnCtxSmem {
+  static constexpr int kStage = 64 * 128 + 128 * 128;  // x tile + (K|V) weight tile
+  static constexpr int kKs = 64 * 65 * 4;
+  static constexpr int kPs = 64 * 72 * 2;
+  static constexpr int kVs = 64 * 72 * 2;
+  static constexpr int kVec = 4 * 64 * 4;  // m_run, alpha, S, spare
+  static constexpr int kBytes = 2 * kStage + kKs + kPs + kVs + kVec;
+};
+
+__global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  float* Ks = reinterpret_cast<float*>(smem + 2 * AttnCtxSmem::kStage);
+  __half* Ps = reinterpret_cast<__half*>(smem + 2 * AttnCtxSmem::kStage + AttnCtxSmem::kKs);
+  __half* Vs = reinterpret_cast<__half*>(smem + 2 * AttnCtxSmem::kStage + AttnCtxSmem::kKs + AttnCtxSmem::kPs);
+  float* m_run = reinterpret_cast<float*>(smem + 2 * AttnCtxSmem::kStage + AttnCtxSmem::kKs + AttnCtxSmem::kPs +
+                                          AttnCtxSmem::kVs);
+  float* alpha = m_run + 64;
+  float* s_run = m_run + 128;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int C = p.C, N = p.N;
+  const int cb = C >> 6;
+  const int chunk = blockIdx.x;
+  const int dblk = blockIdx.y / cb, eblk = blockIdx.y - dblk * cb;
+  const int b = blockIdx.z;
+  const int pix_begin = chunk * p.tiles_per_chunk * 64;
+  int ntiles = p.tiles_per_chunk;
+  {
+    const int remaining = (N - pix_begin + 63) / 64;
+    if (ntiles > remaining) ntiles = remaining;
+  }
+  const __half* xb = p.x + (size_t)b * N * C;
+  const float2* stb = p.stats + (size_t)b * N;
+
+  if (tid < 64) {
+    m_run[tid] = -INFINITY;
+    s_run[tid] = 0.f;
+    alpha[tid] = 0.f;
+  }
+
+  float ctx[2][2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ctx[i][j][k] = 0.f;
+
+  const int total = ntiles * cb;
+  const int lchunk = tid & 7;
+
+  auto load = [&](int it, int stage) {
+    const int t = it / cb, cc = it - t * cb;
+    const uint32_t sX = smem_base + stage * AttnCtxSmem::kStage;
+    const uint32_t sW = sX + 64 * 128;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = (tid >> 3) + 32 * i;
+      const int pix = pix_begin + t * 64 + row;
+      const bool ok = pix < N;
+      const __half* src = ok ? xb + (size_t)pix * C + cc * 64 + lchunk * 8 : xb;
+      cp_async16(sX + swz128(row, lchunk), src, ok ? 16 : 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = (tid >> 3) + 32 * i;  // 0..127
+      const int grow = row < 64 ? dblk * 64 + row : C + eblk * 64 + (row - 64);
+      cp_async16(sW + swz128(row, lchunk), p.Wkv + ((size_t)cc * 2 * C + grow) * 64 + lchunk * 8, 16);
+    }
+  };
+
+  float acc[2][4][4];
+  if (total > 0) load(0, 0);
+  cp_async_commit();
+  __syncthreads();  // m_run / s_run initialised
+
+  for (int it = 0; it < total; ++it) {
+    const int t = it / cb, cc = it - t * cb;
+    if (it + 1 < total) load(it + 1, (it + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (cc == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+    }
+    {
+      const uint32_t sX = smem_base + (it & 1) * AttnCtxSmem::kStage;
+      const uint32_t sW = sX + 64 * 128;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t af[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          ldmatrix_x4(af[mt], sX + swz128(wm * 32 + mt * 16 + (lane & 15), ks * 2 + (lane >> 4)));
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          const int n = wn * 32 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+          uint32_t bf[4];
+          ldmatrix_x4(bf, sW + swz128(n, ks * 2 + ((lane >> 3) & 1)));
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma_16816(acc[mt][2 * np], af[mt], bf[0], bf[1]);
+            mma_16816(acc[mt][2 * np + 1], af[mt], bf[2], bf[3]);
+          }
+        }
+      }
+    }
+    if (cc == cb - 1) {
+      // ---- K/V epilogue for this 64-pixel tile ----
+      const int tile_pix = pix_begin + t * 64;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = wm * 32 + mt * 16 + (lane >> 2) + h * 8;
+          const int pix = tile_pix + row;
+          const bool valid = pix < N;
+          float2 st = make_float2(0.f, 0.f);
+          if (valid) st = stb[pix];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const int col = wn * 32 + nt * 8 + (lane & 3) * 2;  // 0..127
+            const int gcol = col < 64 ? dblk * 64 + col : C + eblk * 64 + (col - 64);
+            float v0 = st.y * (acc[mt][nt][2 * h] - st.x * p.u[gcol]) + p.c[gcol];
+            float v1 = st.y * (acc[mt][nt][2 * h + 1] - st.x * p.u[gcol + 1]) + p.c[gcol + 1];
+            if (wn < 2) {
+              if (!valid) {
+                v0 = -INFINITY;
+                v1 = -INFINITY;
+              }
+              acc[mt][nt][2 * h] = v0;
+              acc[mt][nt][2 * h + 1] = v1;
+              Ks[row * 65 + col] = v0;
+              Ks[row * 65 + col + 1] = v1;
+            } else {
+              if (!valid) {
+                v0 = 0.f;
+                v1 = 0.f;
+              }
+              *reinterpret_cast<uint32_t*>(Vs + row * 72 + (col - 64)) = pack_half2(v0, v1);
+            }
+          }
+        }
+      __syncthreads();
+      if (tid < 64) {
+        float tmax = -INFINITY;
+        for (int r = 0; r < 64; ++r) tmax = fmaxf(tmax, Ks[r * 65 + tid]);
+        const float m_old = m_run[tid];
+        const float m_new = fmaxf(m_old, tmax);
+        alpha[tid] = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
+        m_run[tid] = m_new;
+      }
+      __syncthreads();
+      if (wn < 2) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = wm * 32 + mt * 16 + (lane >> 2) + h * 8;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const int col = wn * 32 + nt * 8 + (lane & 3) * 2;
+              const float p0 = __expf(acc[mt][nt][2 * h] - m_run[col]);       // exp(-inf) = 0 for padded rows
+              const float p1 = __expf(acc[mt][nt][2 * h + 1] - m_run[col + 1]);
+              *reinterpret_cast<uint32_t*>(Ps + row * 72 + col) = pack_half2(p0, p1);
+            }
+          }
+      }
+      __syncthreads();
+      if (tid < 64) {
+        float s = 0.f;
+        for (int r = 0; r < 64; ++r) s += __half2float(Ps[r * 72 + tid]);
+        s_run[tid] = s_run[tid] * alpha[tid] + s;
+      }
+      // ---- ctx[d,e] = ctx*alpha[d] + P^T V ; warps 2(d) x 4(e), warp tile 32 x 16 ----
+      {
+        const int wd = warp >> 2, we = warp & 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float a = alpha[wd * 32 + mt * 16 + (lane >> 2) + h * 8];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              ctx[mt][nt][2 * h] *= a;
+              ctx[mt][nt][2 * h + 1] *= a;
+            }
+          }
+        const uint32_t sP = smem_u32(Ps), sV = smem_u32(Vs);
+        const int j = lane >> 3;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t bf[4];
+          {
+            const int prow = ks * 16 + (lane & 7) + 8 * (j & 1);
+            const int ecol = we * 16 + 8 * (j >> 1);
+            ldmatrix_x4_trans(bf, sV + (prow * 72 + ecol) * 2);
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t af[4];
+            const int prow = ks * 16 + (lane & 7) + 8 * (j >> 1);
+            const int dcol = wd * 32 + mt * 16 + 8 * (j & 1);
+            ldmatrix_x4_trans(af, sP + (prow * 72 + dcol) * 2);
+            mma_16816(ctx[mt][0], af, bf[0], bf[1]);
+            mma_16816(ctx[mt][1], af, bf[2], bf[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+  // ---- write split partials ----
+  {
+    const int wd = warp >> 2, we = warp & 3;
+    float* dst = p.part_ctx + ((size_t)b * p.nchunks + chunk) * C * C;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int d = dblk * 64 + wd * 32 + mt * 16 + (lane >> 2) + h * 8;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int e = eblk * 64 + we * 16 + nt * 8 + (lane & 3) * 2;
+          *reinterpret_cast<float2*>(dst + (size_t)d * C + e) = make_float2(ctx[mt][nt][2 * h], ctx[mt][nt][2 * h + 1]);
+        }
+      }
+    if (eblk == 0 && tid < 64) {
+      const size_t o = ((size_t)b * p.nchunks + chunk) * C + dblk * 64 + tid;
+      p.part_m[o] = m_run[tid];
+      p.part_s[o] = s_run[tid];
+    }
+  }
+}
+
+// ctxn[b][d][e] = sum_c part_ctx[b][c][d][e] * exp(m_c[d]-m[d]) / sum_c part_s[b][c][d]*exp(m_c[d]-m[d])
+__global__ void attn_combine_kernel(const float* __restrict__ part_ctx, const float* __restrict__ part_m,
+                                    const float* __restrict__ part_s, int C, int nchunks,
+                                    float* __restrict__ ctxn) {
+  const int d = blockIdx.x, b = blockIdx.y;
+  const float* pm = part_m + (size_t)b * nchunks * C + d;
+  const float* ps = part_s + (size_t)b * nchunks * C + d;
+  float m = -INFINITY;
+  for (int c = 0; c < nchunks; ++c) m = fmaxf(m, pm[(size_t)c * C]);
+  float S = 0.f;
+  for (int c = 0; c < nchunks; ++c) S += ps[(size_t)c * C] * __expf(pm[(size_t)c * C] - m);
+  const float inv = 1.f / S;
+  for (int e = threadIdx.x; e < C; e += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < nchunks; ++c)
+      a += part_ctx[(((size_t)b * nchunks + c) * C + d) * C + e] * __expf(pm[(size_t)c * C] - m);
+    ctxn[((size_t)b * C + d) * C + e] = a * inv;
+  }
+}
+
+// Batched fp32 GEMM  Cout[b][m][n] = sum_k At[b][k][m] * Bm[b][k][n]  (M, N, K multiples of 64/64/16).
+__global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ At, const float* __restrict__ Bm,
+                                                       float* __restrict__ Cout, int M, int N, int K,
+                                                       long long sA, long long sB, long long sC) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int b = blockIdx.z;
+  At += (size_t)b * sA;
+  Bm += (size_t)b * sB;
+  Cout += (size_t)b * sC;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i >> 6, mm = i & 63;
+      As[kk][mm] = At[(size_t)(k0 + kk) * M + m0 + mm];
+      Bs[kk][mm] = Bm[(size_t)(k0 + kk) * N + n0 + mm];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Cout[(size_t)(m0 + ty * 4 + i) * N + n0 + tx * 4 + j] = acc[i][j];
+}
+
+// Per (image, output row o): Mg16 = half(M[o][:] * g), um = rowsum(float(Mg16)), cm = M[o][:].b_ln + b_out[o].
+// Mg16 is written in the conv kernel's weight layout [C/64][C][64] (per image).
+__global__ void attn_finish_kernel(const float* __restrict__ Mf, const float* __restrict__ g,
+                                   const float* __restrict__ bln, const float* __restrict__ bout, int C,
+                                   __half* __restrict__ Mg16, float* __restrict__ um, float* __restrict__ cm) {
+  const int o = blockIdx.x, b = blockIdx.y;
+  const float* row = Mf + ((size_t)b * C + o) * C;
+  __half* dst = Mg16 + (size_t)b * C * C;
+  float su = 0.f, sc = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float m = row[c];
+    const __half hv = __float2half_rn(m * g[c]);
+    dst[((size_t)(c >> 6) * C + o) * 64 + (c & 63)] = hv;
+    su += __half2float(hv);
+    sc += m * bln[c];
+  }
+  __shared__ float r1[32], r2[32];
+  for (int off = 16; off > 0; off >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, off);
+    sc += __shfl_xor_sync(0xffffffffu, sc, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    r1[threadIdx.x >> 5] = su;
+    r2[threadIdx.x >> 5] = sc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c2 = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      a += r1[i];
+      c2 += r2[i];
+    }
+    um[(size_t)b * C + o] = a;
+    cm[(size_t)b * C + o] = c2 + bout[o];
+  }
+}
+
+}  // namespace cdc

@@ -1,0 +1,1357 @@
+// CDC denoiser engine: weight registry + repack, layer plan, workspace arena, launches, C ABI.
+//
+// Mirrors the reference's module structure (epsilonparam/modules/unet.py:18-124,
+// xparam/modules/unet.py:19-135) as a flat list of kernel launches:
+//   pack_input -> [ResnetBlock x2 -> LinearAttention -> Downsample] x levels -> mid -> [cat skip ->
+//   ResnetBlock x2 -> LinearAttention -> Upsample] x levels -> LayerNorm+conv7x7 (+DDIM update)
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/cdc_b200.h"
+#include "attn.cuh"
+#include "igemm_hmma.cuh"
+#include "misc.cuh"
+
+using namespace cdc;
+
+namespace {
+
+std::string g_create_error;
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+// ---------------------------------------------------------------- weight blob
+struct Blob {
+  std::vector<uint8_t> host;
+  size_t reserve(size_t bytes) {
+    size_t off = (host.size() + 255) & ~size_t(255);
+    host.resize(off + bytes, 0);
+    return off;
+  }
+  template <typename T>
+  T* at(size_t off) { return reinterpret_cast<T*>(host.data() + off); }
+};
+
+struct ConvW {      // one convolution-shaped weight set in kernel layout
+  size_t w = 0;     // fp16 [chunk][N][64] (x4 phases for transposed conv)
+  size_t bias = 0;  // fp32 [N]
+  int nchunks = 0;
+  int N = 0;
+  double macs_per_row = 0;  // algorithmic MACs per output row (pixel)
+};
+struct BlockW {
+  ConvW conv;
+  size_t g = 0, b = 0;
+};
+struct ResW {
+  BlockW b1, b2;
+  bool has_res = false;
+  ConvW res;
+  int shift_off = 0;  // offset of this block's rows in the concatenated timestep-MLP output
+  int cin = 0, cout = 0;
+};
+struct AttnW {
+  int C = 0;
+  size_t wkv = 0, u = 0, c = 0;          // fp16 [C/64][2C][64], fp32 [2C], fp32 [2C]
+  size_t wq = 0, woT = 0;                // fp32 [C][C] (scale folded), fp32 [C][C] transposed
+  size_t g = 0, bln = 0, bout = 0;       // fp32 [C]
+};
+
+struct Level {
+  ResW rb0, rb1;
+  AttnW attn;
+  bool has_resample = false;
+  ConvW resample;
+  int cin = 0, cout = 0;
+};
+
+// ---------------------------------------------------------------- plan
+enum OpKind { OP_PACK, OP_CONV, OP_TIME, OP_ATTN_CTX, OP_COMBINE, OP_SGEMM, OP_FINISH, OP_FINAL, OP_ADVANCE };
+
+struct Op {
+  int kind = 0;
+  std::string name;
+  // conv
+  ConvParams conv{};
+  int bm = 0, bn = 0, epi = 0;
+  dim3 grid{1, 1, 1};
+  // attention
+  AttnCtxParams actx{};
+  struct { const float *pc, *pm, *ps; int C, nchunks; float* out; } comb{};
+  struct { const float *At, *Bm; float* Cout; int M, N, K; long long sA, sB, sC; } sg{};
+  struct { const float *Mf, *g, *bln, *bout; int C; __half* Mg; float *um, *cm; } fin{};
+  // debug view of the op's fp16 NHWC output (if any)
+  const __half* dbg = nullptr;
+  int dC = 0, dH = 0, dW = 0;
+  double flops = 0;
+};
+
+struct Arena {
+  size_t top = 0, peak = 0;
+  bool no_reuse = false;
+  std::vector<std::pair<size_t, size_t>> free_list;  // (offset, size), sorted by offset
+  size_t alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    for (size_t i = 0; i < free_list.size(); ++i) {
+      if (free_list[i].second >= bytes) {
+        size_t off = free_list[i].first;
+        if (free_list[i].second == bytes) free_list.erase(free_list.begin() + i);
+        else { free_list[i].first += bytes; free_list[i].second -= bytes; }
+        return off;
+      }
+    }
+    size_t off = top;
+    top += bytes;
+    peak = std::max(peak, top);
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    if (no_reuse) return;
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    auto it = std::lower_bound(free_list.begin(), free_list.end(), std::make_pair(off, size_t(0)));
+    it = free_list.insert(it, {off, bytes});
+    // coalesce with next / previous
+    size_t i = it - free_list.begin();
+    if (i + 1 < free_list.size() && free_list[i].first + free_list[i].second == free_list[i + 1].first) {
+      free_list[i].second += free_list[i + 1].second;
+      free_list.erase(free_list.begin() + i + 1);
+    }
+    if (i > 0 && free_list[i - 1].first + free_list[i - 1].second == free_list[i].first) {
+      free_list[i - 1].second += free_list[i].second;
+      free_list.erase(free_list.begin() + i);
+      --i;
+    }
+    if (free_list[i].first + free_list[i].second == top) {
+      top = free_list[i].first;
+      free_list.erase(free_list.begin() + i);
+    }
+  }
+};
+
+struct Act {  // fp16 NHWC activation in the workspace
+  size_t off = 0, bytes = 0;
+  int C = 0, H = 0, W = 0;
+};
+
+struct Plan {
+  int B = 0, H = 0, W = 0;
+  uint8_t* ws = nullptr;
+  size_t total_bytes = 0;
+  std::vector<Op> ops;
+  // persistent region
+  std::vector<size_t> ctx_off;     // fp16 NHWC context per level (level 0 of the eps variant: fp32 NCHW copy)
+  size_t shifts_off = 0;
+  int pack_op = -1, time_op = -1, final_op = -1;
+  double flops = 0;
+  // captured step graph
+  cudaGraphExec_t graph = nullptr;
+  const float* graph_x = nullptr;
+  int graph_pred = -1, graph_clip = -1;
+};
+
+}  // namespace
+
+struct cdc_engine {
+  cdc_config cfg{};
+  int device = 0;
+  std::string err;
+  std::map<std::string, HostTensor> weights;
+  bool finalized = false;
+  bool dry = false;  // created with device == -1: planning only
+  bool debug_no_reuse = false;
+  int mainloop = 0;
+  // derived structure
+  std::vector<int> dims, cdims;
+  bool fold_ctx0 = false;  // small level-0 context folded into the packed input (eps demo)
+  int R = 0;               // total timestep-shift rows
+  // weights
+  Blob blob;
+  uint8_t* dblob = nullptr;
+  size_t dblob_bytes = 0;
+  std::vector<Level> downs, ups;
+  ResW mid1, mid2;
+  AttnW mid_attn;
+  size_t t_w1 = 0, t_b1 = 0, t_w2 = 0, t_b2 = 0, t_wcat = 0, t_bcat = 0;
+  size_t f_g = 0, f_b = 0, f_w = 0, f_bias = 0;
+  // plans
+  std::map<std::tuple<int, int, int, uintptr_t>, std::unique_ptr<Plan>> plans;
+  // schedule
+  cdc_step_coef* d_table = nullptr;
+  int table_cap = 0, S = 0;
+  int* d_step = nullptr;
+  // context state
+  bool ctx_set = false;
+  int ctx_B = 0, ctx_H = 0, ctx_W = 0;
+  uintptr_t ctx_ws = 0;
+  Plan* last_plan = nullptr;
+};
+
+namespace {
+
+int fail(cdc_engine* e, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(e, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _err = (expr);                                                                    \
+    if (_err != cudaSuccess)                                                                      \
+      return fail(e, CDC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_err), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+T* dptr(cdc_engine* e, size_t off) { return reinterpret_cast<T*>(e->dblob + off); }
+
+// ---------------------------------------------------------------- weight lookup helpers
+const HostTensor* find(cdc_engine* e, const std::string& key, std::initializer_list<int64_t> shape, int* rc) {
+  auto it = e->weights.find(key);
+  if (it == e->weights.end()) {
+    *rc = fail(e, CDC_ERR_MISSING, "missing weight '%s'", key.c_str());
+    return nullptr;
+  }
+  const HostTensor& t = it->second;
+  std::vector<int64_t> want(shape);
+  if (t.shape != want) {
+    std::string got, exp;
+    for (auto v : t.shape) got += std::to_string(v) + ",";
+    for (auto v : want) exp += std::to_string(v) + ",";
+    *rc = fail(e, CDC_ERR_MISSING, "weight '%s' has shape [%s] expected [%s]", key.c_str(), got.c_str(), exp.c_str());
+    return nullptr;
+  }
+  return &t;
+}
+
+size_t put_f32(cdc_engine* e, const float* src, size_t n) {
+  size_t off = e->blob.reserve(n * 4);
+  memcpy(e->blob.at<float>(off), src, n * 4);
+  return off;
+}
+
+struct SegSpec {  // how one K-segment of a conv maps onto the reference's OIHW input channels
+  int C;          // padded channel count of the segment tensor (multiple of 64)
+  int kh, kw;
+  int mode;       // 0: channel k of chunk cc at tap (ty,tx) <- W[o][coff + cc*64+k][ty][tx]
+                  // 1: packed input X0: k = kx*8 + c (c < creal) at vertical tap ty <- W[o][coff + c][ty][kx]  (kw==1)
+                  // 2: packed input X0, 1x1 conv: k = 3*8 + c <- W[o][coff + c][0][0]
+  int coff;       // first reference input channel of this segment
+  int creal;      // real channels (mode 1/2)
+};
+
+// OIHW conv weight -> [chunk][N][64] fp16
+int pack_conv(cdc_engine* e, const std::string& key, int N, int Cin_ref, int KH, int KW,
+              const std::vector<SegSpec>& segs, bool with_bias, ConvW* out) {
+  int rc = 0;
+  const HostTensor* w = find(e, key + ".weight", {N, Cin_ref, KH, KW}, &rc);
+  if (!w) return rc;
+  int nchunks = 0;
+  for (auto& s : segs) nchunks += s.kh * s.kw * (s.C / 64);
+  out->nchunks = nchunks;
+  out->N = N;
+  out->macs_per_row = (double)N * Cin_ref * KH * KW;
+  out->w = e->blob.reserve((size_t)nchunks * N * 64 * 2);
+  std::vector<__half> tmp((size_t)nchunks * N * 64, __float2half(0.f));
+  int q = 0;
+  for (auto& s : segs) {
+    for (int ty = 0; ty < s.kh; ++ty)
+      for (int tx = 0; tx < s.kw; ++tx)
+        for (int cc = 0; cc < s.C / 64; ++cc, ++q)
+          for (int o = 0; o < N; ++o)
+            for (int k = 0; k < 64; ++k) {
+              float v = 0.f;
+              if (s.mode == 0) {
+                const int c = s.coff + cc * 64 + k;
+                v = w->data[(((size_t)o * Cin_ref + c) * KH + ty) * KW + tx];
+              } else if (s.mode == 1) {
+                const int kx = k >> 3, c = k & 7;
+                if (kx < KW && c < s.creal) v = w->data[(((size_t)o * Cin_ref + s.coff + c) * KH + ty) * KW + kx];
+              } else {
+                const int kx = k >> 3, c = k & 7;
+                if (kx == 3 && c < s.creal) v = w->data[((size_t)o * Cin_ref + s.coff + c)];
+              }
+              tmp[((size_t)q * N + o) * 64 + k] = __float2half_rn(v);
+            }
+  }
+  memcpy(e->blob.at<__half>(out->w), tmp.data(), tmp.size() * 2);
+  if (with_bias) {
+    const HostTensor* b = find(e, key + ".bias", {N}, &rc);
+    if (!b) return rc;
+    out->bias = put_f32(e, b->data.data(), N);
+  }
+  return 0;
+}
+
+// ConvTranspose2d(C,C,4,2,1) weight [Cin][Cout][4][4] -> 4 phases x [tap(2x2)*Cin/64][Cout][64]
+int pack_convT(cdc_engine* e, const std::string& key, int Cin, int Cout, ConvW* out) {
+  int rc = 0;
+  const HostTensor* w = find(e, key + ".weight", {Cin, Cout, 4, 4}, &rc);
+  if (!w) return rc;
+  const HostTensor* b = find(e, key + ".bias", {Cout}, &rc);
+  if (!b) return rc;
+  const int cpt = Cin / 64;
+  out->nchunks = 4 * cpt;
+  out->N = Cout;
+  out->macs_per_row = (double)Cout * Cin * 4;  // per OUTPUT pixel: 2x2 taps
+  std::vector<__half> tmp((size_t)4 * out->nchunks * Cout * 64);
+  for (int z = 0; z < 4; ++z) {
+    const int py = z >> 1, px = z & 1;
+    int q = 0;
+    for (int ty = 0; ty < 2; ++ty)
+      for (int tx = 0; tx < 2; ++tx)
+        for (int cc = 0; cc < cpt; ++cc, ++q) {
+          const int ky = 3 - 2 * ty - py, kx = 3 - 2 * tx - px;
+          for (int o = 0; o < Cout; ++o)
+            for (int k = 0; k < 64; ++k) {
+              const int c = cc * 64 + k;
+              tmp[(((size_t)z * out->nchunks + q) * Cout + o) * 64 + k] =
+                  __float2half_rn(w->data[(((size_t)c * Cout + o) * 4 + ky) * 4 + kx]);
+            }
+        }
+  }
+  out->w = e->blob.reserve(tmp.size() * 2);
+  memcpy(e->blob.at<__half>(out->w), tmp.data(), tmp.size() * 2);
+  out->bias = put_f32(e, b->data.data(), Cout);
+  return 0;
+}
+
+int pack_ln(cdc_engine* e, const std::string& key, int C, size_t* g, size_t* b) {
+  int rc = 0;
+  const HostTensor* tg = find(e, key + ".g", {1, C, 1, 1}, &rc);
+  if (!tg) return rc;
+  const HostTensor* tb = find(e, key + ".b", {1, C, 1, 1}, &rc);
+  if (!tb) return rc;
+  *g = put_f32(e, tg->data.data(), C);
+  *b = put_f32(e, tb->data.data(), C);
+  return 0;
+}
+
+int pack_resnet(cdc_engine* e, const std::string& p, int cin, int cout, int k1,
+                const std::vector<SegSpec>& segs1, const std::vector<SegSpec>& segs_res, ResW* out,
+                std::vector<float>* wcat, std::vector<float>* bcat) {
+  int rc;
+  out->cin = cin;
+  out->cout = cout;
+  if ((rc = pack_conv(e, p + "block1.block.0", cout, cin, k1, k1, segs1, true, &out->b1.conv))) return rc;
+  if ((rc = pack_ln(e, p + "block1.block.1", cout, &out->b1.g, &out->b1.b))) return rc;
+  std::vector<SegSpec> s2 = {{cout, 3, 3, 0, 0, 0}};
+  if ((rc = pack_conv(e, p + "block2.block.0", cout, cout, 3, 3, s2, true, &out->b2.conv))) return rc;
+  if ((rc = pack_ln(e, p + "block2.block.1", cout, &out->b2.g, &out->b2.b))) return rc;
+  out->has_res = cin != cout;
+  if (out->has_res) {
+    if ((rc = pack_conv(e, p + "res_conv", cout, cin, 1, 1, segs_res, true, &out->res))) return rc;
+  }
+  const int dim = e->cfg.dim;
+  const HostTensor* mw = find(e, p + "mlp.1.weight", {cout, dim}, &rc);
+  if (!mw) return rc;
+  const HostTensor* mb = find(e, p + "mlp.1.bias", {cout}, &rc);
+  if (!mb) return rc;
+  out->shift_off = (int)bcat->size();
+  wcat->insert(wcat->end(), mw->data.begin(), mw->data.end());
+  bcat->insert(bcat->end(), mb->data.begin(), mb->data.end());
+  return 0;
+}
+
+int pack_attn(cdc_engine* e, const std::string& p, int C, AttnW* out) {
+  int rc = 0;
+  const HostTensor* g = find(e, p + "fn.norm.g", {1, C, 1, 1}, &rc);
+  if (!g) return rc;
+  const HostTensor* bl = find(e, p + "fn.norm.b", {1, C, 1, 1}, &rc);
+  if (!bl) return rc;
+  const HostTensor* wqkv = find(e, p + "fn.fn.to_qkv.weight", {3 * C, C, 1, 1}, &rc);
+  if (!wqkv) return rc;
+  const HostTensor* wo = find(e, p + "fn.fn.to_out.weight", {C, C, 1, 1}, &rc);
+  if (!wo) return rc;
+  const HostTensor* bo = find(e, p + "fn.fn.to_out.bias", {C}, &rc);
+  if (!bo) return rc;
+  out->C = C;
+  const int cb = C / 64;
+  std::vector<__half> wkv((size_t)cb * 2 * C * 64);
+  std::vector<float> u(2 * C, 0.f), cv(2 * C, 0.f);
+  for (int r = 0; r < 2 * C; ++r) {
+    const float* row = &wqkv->data[(size_t)(C + r) * C];  // rows C..3C-1 of to_qkv = [k; v]
+    double su = 0, sc = 0;
+    for (int c = 0; c < C; ++c) {
+      const __half hv = __float2half_rn(row[c] * g->data[c]);
+      wkv[((size_t)(c >> 6) * 2 * C + r) * 64 + (c & 63)] = hv;
+      su += __half2float(hv);
+      sc += (double)row[c] * bl->data[c];
+    }
+    u[r] = (float)su;
+    cv[r] = (float)sc;
+  }
+  out->wkv = e->blob.reserve(wkv.size() * 2);
+  memcpy(e->blob.at<__half>(out->wkv), wkv.data(), wkv.size() * 2);
+  out->u = put_f32(e, u.data(), u.size());
+  out->c = put_f32(e, cv.data(), cv.size());
+  const float scale = 1.0f / sqrtf((float)C);
+  std::vector<float> wq((size_t)C * C), woT((size_t)C * C);
+  for (int d = 0; d < C; ++d)
+    for (int c = 0; c < C; ++c) wq[(size_t)d * C + c] = wqkv->data[(size_t)d * C + c] * scale;
+  for (int o = 0; o < C; ++o)
+    for (int ee = 0; ee < C; ++ee) woT[(size_t)ee * C + o] = wo->data[(size_t)o * C + ee];
+  out->wq = put_f32(e, wq.data(), wq.size());
+  out->woT = put_f32(e, woT.data(), woT.size());
+  out->g = put_f32(e, g->data.data(), C);
+  out->bln = put_f32(e, bl->data.data(), C);
+  out->bout = put_f32(e, bo->data.data(), C);
+  return 0;
+}
+
+// ---------------------------------------------------------------- kernel dispatch
+template <int BM, int BN, int EPI>
+cudaError_t launch_igemm_t(const Op& op, cudaStream_t st) {
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(igemm_hmma_kernel<BM, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           IgemmSmem<BM, BN>::kBytes);
+    if (err != cudaSuccess) return err;
+    attr_set[dev] = true;
+  }
+  igemm_hmma_kernel<BM, BN, EPI><<<op.grid, 256, IgemmSmem<BM, BN>::kBytes, st>>>(op.conv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_igemm(const Op& op, cudaStream_t st) {
+#define CASE(BM_, BN_, EPI_) \
+  if (op.bm == BM_ && op.bn == BN_ && op.epi == EPI_) return launch_igemm_t<BM_, BN_, EPI_>(op, st);
+  CASE(128, 64, EPI_BIAS) CASE(128, 128, EPI_BIAS) CASE(128, 64, EPI_AFFINE) CASE(128, 128, EPI_AFFINE)
+  CASE(128, 64, EPI_LN_SHIFT) CASE(128, 128, EPI_LN_SHIFT) CASE(64, 192, EPI_LN_SHIFT) CASE(64, 256, EPI_LN_SHIFT)
+  CASE(64, 320, EPI_LN_SHIFT) CASE(64, 384, EPI_LN_SHIFT)
+  CASE(128, 64, EPI_LN_RES) CASE(128, 128, EPI_LN_RES) CASE(64, 192, EPI_LN_RES) CASE(64, 256, EPI_LN_RES)
+  CASE(64, 320, EPI_LN_RES) CASE(64, 384, EPI_LN_RES)
+#undef CASE
+  return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------- plan builder
+struct Builder {
+  cdc_engine* e;
+  Plan* pl;
+  Arena arena;
+  size_t arena_base = 0;
+  int B, H, W;
+
+  template <typename T>
+  T* ws(size_t off) { return reinterpret_cast<T*>(pl->ws + off); }  // valid arithmetic even for ws == nullptr (dry run)
+
+  Act new_act(int C, int h, int w) {
+    Act a;
+    a.C = C; a.H = h; a.W = w;
+    a.bytes = (size_t)B * h * w * C * 2;
+    a.off = arena_base + arena.alloc(a.bytes);
+    return a;
+  }
+  void drop(const Act& a) { arena.release(a.off - arena_base, a.bytes); }
+  size_t raw_alloc(size_t bytes) { return arena_base + arena.alloc(bytes); }
+  void raw_free(size_t off, size_t bytes) { arena.release(off - arena_base, bytes); }
+
+  struct SegIn {
+    Act a;
+    int kh, kw, dy0, dx0;
+  };
+
+  // generic conv op. stride / phases describe resampling; epi selects the fused epilogue.
+  Op& conv(const std::string& name, const std::vector<SegIn>& segs, const ConvW& w, int epi, const Act& out,
+           int stride, int phases) {
+    pl->ops.emplace_back();
+    Op& op = pl->ops.back();
+    op.kind = OP_CONV;
+    op.name = name;
+    ConvParams& p = op.conv;
+    p.nseg = (int)segs.size();
+    int total = 0;
+    for (int i = 0; i < p.nseg; ++i) {
+      p.seg[i].src = ws<__half>(segs[i].a.off);
+      p.seg[i].C = segs[i].a.C;
+      p.seg[i].kh = segs[i].kh;
+      p.seg[i].kw = segs[i].kw;
+      p.seg[i].dy0 = segs[i].dy0;
+      p.seg[i].dx0 = segs[i].dx0;
+      p.seg[i].nchunk = segs[i].kh * segs[i].kw * (segs[i].a.C / 64);
+      total += p.seg[i].nchunk;
+    }
+    p.Hs = segs[0].a.H;
+    p.Ws = segs[0].a.W;
+    if (phases) { p.Ho = p.Hs; p.Wo = p.Ws; }
+    else { p.Ho = out.H; p.Wo = out.W; }
+    p.stride = stride;
+    p.rows_per_group = B * p.Ho * p.Wo;
+    p.groups = 1;
+    p.w_group_stride = 0;
+    p.W = dptr<__half>(e, w.w);
+    p.Ntot = w.N;
+    p.total_chunks = total;
+    p.phases = phases;
+    p.w_phase_stride = (long long)total * w.N * 64;
+    p.out = ws<__half>(out.off);
+    p.out_H = out.H;
+    p.out_W = out.W;
+    p.out_sy = phases ? 2 : 1;
+    p.out_sx = phases ? 2 : 1;
+    p.bias = w.bias ? dptr<float>(e, w.bias) : nullptr;
+    op.epi = epi;
+    const bool ln = epi == EPI_LN_SHIFT || epi == EPI_LN_RES;
+    if (ln) { op.bn = w.N; op.bm = w.N <= 128 ? 128 : 64; }
+    else { op.bn = (w.N % 128 == 0) ? 128 : 64; op.bm = 128; }
+    op.grid = dim3((p.rows_per_group + op.bm - 1) / op.bm, w.N / op.bn, phases ? 4 : 1);
+    op.dbg = p.out;
+    op.dC = w.N; op.dH = out.H; op.dW = out.W;
+    op.flops = 2.0 * w.macs_per_row * (double)B * out.H * out.W;
+    return op;
+  }
+
+  // ResnetBlock: block1 (+temb shift) -> block2 (+residual). Returns the output activation.
+  Act resnet(const std::string& name, const std::vector<SegIn>& segs1, const std::vector<SegIn>& segs_res,
+             const ResW& w, int h, int wd, float2* stats_out) {
+    Act h1 = new_act(w.cout, h, wd);
+    {
+      Op& op = conv(name + "block1", segs1, w.b1.conv, EPI_LN_SHIFT, h1, 1, 0);
+      op.conv.ln_g = dptr<float>(e, w.b1.g);
+      op.conv.ln_b = dptr<float>(e, w.b1.b);
+      op.conv.shift = ws<float>(pl->shifts_off) + w.shift_off;
+      op.conv.shift_stride = e->R;
+    }
+    Act r;
+    bool own_r = false;
+    if (w.has_res) {
+      r = new_act(w.cout, h, wd);
+      own_r = true;
+      conv(name + "res_conv", segs_res, w.res, EPI_BIAS, r, 1, 0);
+    }
+    Act out = new_act(w.cout, h, wd);
+    {
+      std::vector<SegIn> s2 = {{h1, 3, 3, -1, -1}};
+      Op& op = conv(name + "block2", s2, w.b2.conv, EPI_LN_RES, out, 1, 0);
+      op.conv.ln_g = dptr<float>(e, w.b2.g);
+      op.conv.ln_b = dptr<float>(e, w.b2.b);
+      if (w.has_res) {
+        op.conv.res = ws<__half>(r.off);
+        op.conv.res_C0 = w.cout;
+        op.conv.res2 = nullptr;
+      } else {
+        // identity residual: the (possibly concatenated) block input itself
+        op.conv.res = ws<__half>(segs_res[0].a.off);
+        op.conv.res_C0 = segs_res[0].a.C;
+        op.conv.res2 = segs_res.size() > 1 ? ws<__half>(segs_res[1].a.off) : nullptr;
+      }
+      op.conv.stats_out = stats_out;
+    }
+    drop(h1);
+    if (own_r) drop(r);
+    return out;
+  }
+
+  Act attention(const std::string& name, const Act& x, float2* stats, size_t stats_off, size_t stats_bytes,
+                const AttnW& w) {
+    const int C = w.C, N = x.H * x.W, cb = C / 64;
+    const int ntiles = (N + 63) / 64;
+    int nchunks = std::min(ntiles, std::max(1, 296 / (B * cb * cb)));
+    const int tpc = (ntiles + nchunks - 1) / nchunks;
+    nchunks = (ntiles + tpc - 1) / tpc;
+    const size_t pc_b = (size_t)B * nchunks * C * C * 4, pv_b = (size_t)B * nchunks * C * 4;
+    const size_t pc = raw_alloc(pc_b), pm = raw_alloc(pv_b), ps = raw_alloc(pv_b);
+    {
+      pl->ops.emplace_back();
+      Op& op = pl->ops.back();
+      op.kind = OP_ATTN_CTX;
+      op.name = name + "ctx";
+      op.actx.x = ws<__half>(x.off);
+      op.actx.stats = stats;
+      op.actx.Wkv = dptr<__half>(e, w.wkv);
+      op.actx.u = dptr<float>(e, w.u);
+      op.actx.c = dptr<float>(e, w.c);
+      op.actx.C = C;
+      op.actx.N = N;
+      op.actx.tiles_per_chunk = tpc;
+      op.actx.nchunks = nchunks;
+      op.actx.part_ctx = ws<float>(pc);
+      op.actx.part_m = ws<float>(pm);
+      op.actx.part_s = ws<float>(ps);
+      op.grid = dim3(nchunks, cb * cb, B);
+      // to_qkv 1x1 (3C x C per pixel) + the two einsums (2 * C*C per pixel) + to_out (C x C per pixel)
+      op.flops = 2.0 * (double)B * N * C * (3.0 * C + 2.0 * C + C);
+    }
+    const size_t cc_b = (size_t)B * C * C * 4;
+    const size_t ctxn = raw_alloc(cc_b);
+    {
+      pl->ops.emplace_back();
+      Op& op = pl->ops.back();
+      op.kind = OP_COMBINE;
+      op.name = name + "combine";
+      op.comb = {ws<float>(pc), ws<float>(pm), ws<float>(ps), C, nchunks, ws<float>(ctxn)};
+      op.grid = dim3(C, B, 1);
+    }
+    raw_free(pc, pc_b); raw_free(pm, pv_b); raw_free(ps, pv_b);
+    const size_t T = raw_alloc(cc_b);
+    {
+      pl->ops.emplace_back();
+      Op& op = pl->ops.back();
+      op.kind = OP_SGEMM;
+      op.name = name + "T";
+      op.sg = {ws<float>(ctxn), dptr<float>(e, w.wq), ws<float>(T), C, C, C, (long long)C * C, 0, (long long)C * C};
+      op.grid = dim3(C / 64, C / 64, B);
+    }
+    raw_free(ctxn, cc_b);
+    const size_t Mf = raw_alloc(cc_b);
+    {
+      pl->ops.emplace_back();
+      Op& op = pl->ops.back();
+      op.kind = OP_SGEMM;
+      op.name = name + "M";
+      op.sg = {dptr<float>(e, w.woT), ws<float>(T), ws<float>(Mf), C, C, C, 0, (long long)C * C, (long long)C * C};
+      op.grid = dim3(C / 64, C / 64, B);
+    }
+    raw_free(T, cc_b);
+    const size_t mg_b = (size_t)B * C * C * 2, v_b = (size_t)B * C * 4;
+    const size_t Mg = raw_alloc(mg_b), um = raw_alloc(v_b), cm = raw_alloc(v_b);
+    {
+      pl->ops.emplace_back();
+      Op& op = pl->ops.back();
+      op.kind = OP_FINISH;
+      op.name = name + "finish";
+      op.fin = {ws<float>(Mf), dptr<float>(e, w.g), dptr<float>(e, w.bln), dptr<float>(e, w.bout), C,
+                ws<__half>(Mg), ws<float>(um), ws<float>(cm)};
+      op.grid = dim3(C, B, 1);
+    }
+    raw_free(Mf, cc_b);
+    Act out = new_act(C, x.H, x.W);
+    {
+      ConvW cw;
+      cw.w = 0; cw.bias = 0; cw.N = C; cw.nchunks = cb; cw.macs_per_row = 0;
+      std::vector<SegIn> s = {{x, 1, 1, 0, 0}};
+      Op& op = conv(name + "out", s, cw, EPI_AFFINE, out, 1, 0);
+      ConvParams& p = op.conv;
+      p.W = ws<__half>(Mg);
+      p.groups = B;
+      p.rows_per_group = N;
+      p.w_group_stride = (long long)C * C;
+      p.stats_in = stats;
+      p.aff_u = ws<float>(um);
+      p.aff_c = ws<float>(cm);
+      p.aff_group_stride = C;
+      p.res = ws<__half>(x.off);
+      p.res_C0 = C;
+      p.res2 = nullptr;
+      p.bias = nullptr;
+      op.grid = dim3(B * ((N + op.bm - 1) / op.bm), C / op.bn, 1);
+      op.flops = 0;
+    }
+    raw_free(Mg, mg_b); raw_free(um, v_b); raw_free(cm, v_b);
+    raw_free(stats_off, stats_bytes);
+    return out;
+  }
+};
+
+int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
+  const cdc_config& cfg = e->cfg;
+  const int L = cfg.n_levels;
+  pl->B = B; pl->H = H; pl->W = W; pl->ws = wsp;
+  Builder bd{e, pl};
+  bd.B = B; bd.H = H; bd.W = W;
+  bd.arena.no_reuse = e->debug_no_reuse;
+
+  // ---- persistent region: context + shifts ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+  pl->ctx_off.clear();
+  for (int l = 0; l < cfg.n_context; ++l) {
+    const int c = e->cdims[l], h = H >> l, w = W >> l;
+    if (l == 0 && e->fold_ctx0) pl->ctx_off.push_back(take((size_t)B * c * h * w * 4));  // fp32 NCHW copy
+    else pl->ctx_off.push_back(take((size_t)B * c * h * w * 2));
+  }
+  pl->shifts_off = take((size_t)B * e->R * 4);
+  bd.arena_base = off;
+
+  // ---- ops ----
+  {
+    pl->ops.emplace_back();
+    Op& op = pl->ops.back();
+    op.kind = OP_TIME;
+    op.name = "time_mlp";
+    pl->time_op = (int)pl->ops.size() - 1;
+  }
+  Act x0 = bd.new_act(64, H, W);
+  {
+    pl->ops.emplace_back();
+    Op& op = pl->ops.back();
+    op.kind = OP_PACK;
+    op.name = "pack_input";
+    op.dbg = bd.ws<__half>(x0.off);
+    op.dC = 64; op.dH = H; op.dW = W;
+    pl->pack_op = (int)pl->ops.size() - 1;
+  }
+  auto ctx_act = [&](int l) {
+    Act a;
+    a.off = pl->ctx_off[l]; a.C = e->cdims[l]; a.H = H >> l; a.W = W >> l;
+    a.bytes = 0;
+    return a;
+  };
+  auto new_stats = [&](int h, int w, size_t* o, size_t* bytes) {
+    *bytes = (size_t)B * h * w * 8;
+    *o = bd.raw_alloc(*bytes);
+    return bd.ws<float2>(*o);
+  };
+
+  std::vector<Act> skips;
+  Act x = x0;
+  for (int l = 0; l < L; ++l) {
+    const Level& lv = e->downs[l];
+    const int h = H >> l, w = W >> l;
+    const std::string p = "downs." + std::to_string(l) + ".";
+    std::vector<Builder::SegIn> s1, sr;
+    const bool has_ctx = (l < L - 1) && (l < cfg.n_context);
+    if (l == 0) {
+      s1.push_back({x, 7, 1, -3, 0});
+      sr.push_back({x, 1, 1, 0, 0});
+      if (has_ctx && !e->fold_ctx0) {
+        s1.push_back({ctx_act(0), 7, 7, -3, -3});
+        sr.push_back({ctx_act(0), 1, 1, 0, 0});
+      }
+    } else {
+      s1.push_back({x, 3, 3, -1, -1});
+      sr.push_back({x, 1, 1, 0, 0});
+      if (has_ctx) {
+        s1.push_back({ctx_act(l), 3, 3, -1, -1});
+        sr.push_back({ctx_act(l), 1, 1, 0, 0});
+      }
+    }
+    Act a = bd.resnet(p + "0.", s1, sr, lv.rb0, h, w, nullptr);
+    bd.drop(x);
+    size_t so, sb;
+    float2* st = new_stats(h, w, &so, &sb);
+    std::vector<Builder::SegIn> s2 = {{a, 3, 3, -1, -1}}, sr2 = {{a, 1, 1, 0, 0}};
+    Act bq = bd.resnet(p + "1.", s2, sr2, lv.rb1, h, w, st);
+    bd.drop(a);
+    Act c = bd.attention(p + "2.", bq, st, so, sb, lv.attn);
+    bd.drop(bq);
+    skips.push_back(c);
+    if (lv.has_resample) {
+      Act d = bd.new_act(lv.cout, h / 2, w / 2);
+      std::vector<Builder::SegIn> sd = {{c, 3, 3, -1, -1}};
+      bd.conv(p + "3.down", sd, lv.resample, EPI_BIAS, d, 2, 0);
+      x = d;
+      if (l == 0) { bd.drop(c); }  // the level-0 skip is never consumed (unet.py:102 vs :113)
+    } else {
+      x = c;
+    }
+  }
+  // After the loop: x is either the last level's attention output (== skips.back(), still owned by skips)
+  // mid
+  {
+    const int h = H >> (L - 1), w = W >> (L - 1);
+    std::vector<Builder::SegIn> s1 = {{x, 3, 3, -1, -1}}, sr = {{x, 1, 1, 0, 0}};
+    size_t so, sb;
+    float2* st = new_stats(h, w, &so, &sb);
+    Act a = bd.resnet("mid_block1.", s1, sr, e->mid1, h, w, st);
+    Act c = bd.attention("mid_attn.", a, st, so, sb, e->mid_attn);
+    bd.drop(a);
+    std::vector<Builder::SegIn> s2 = {{c, 3, 3, -1, -1}}, sr2 = {{c, 1, 1, 0, 0}};
+    Act d = bd.resnet("mid_block2.", s2, sr2, e->mid2, h, w, nullptr);
+    bd.drop(c);
+    x = d;
+  }
+  for (int l = 0; l < L - 1; ++l) {
+    const Level& lv = e->ups[l];
+    const int lev = L - 1 - l;
+    const int h = H >> lev, w = W >> lev;
+    const std::string p = "ups." + std::to_string(l) + ".";
+    Act skip = skips[lev];
+    std::vector<Builder::SegIn> s1 = {{x, 3, 3, -1, -1}, {skip, 3, 3, -1, -1}};
+    std::vector<Builder::SegIn> sr = {{x, 1, 1, 0, 0}, {skip, 1, 1, 0, 0}};
+    Act a = bd.resnet(p + "0.", s1, sr, lv.rb0, h, w, nullptr);
+    bd.drop(x);
+    bd.drop(skip);
+    size_t so, sb;
+    float2* st = new_stats(h, w, &so, &sb);
+    std::vector<Builder::SegIn> s2 = {{a, 3, 3, -1, -1}}, sr2 = {{a, 1, 1, 0, 0}};
+    Act bq = bd.resnet(p + "1.", s2, sr2, lv.rb1, h, w, st);
+    bd.drop(a);
+    Act c = bd.attention(p + "2.", bq, st, so, sb, lv.attn);
+    bd.drop(bq);
+    Act u = bd.new_act(lv.cout, h * 2, w * 2);
+    std::vector<Builder::SegIn> su = {{c, 2, 2, 0, 0}};
+    bd.conv(p + "3.up", su, lv.resample, EPI_BIAS, u, 1, 4);
+    bd.drop(c);
+    x = u;
+  }
+  {
+    pl->ops.emplace_back();
+    Op& op = pl->ops.back();
+    op.kind = OP_FINAL;
+    op.name = "final_conv";
+    op.dbg = bd.ws<__half>(x.off);  // debug view: the final conv's INPUT activation
+    op.dC = 64; op.dH = H; op.dW = W;
+    op.flops = 2.0 * (double)B * H * W * cfg.channels * 64 * 49;
+    pl->final_op = (int)pl->ops.size() - 1;
+    // stash input pointer in conv.seg[0].src for the launcher
+    op.conv.seg[0].src = bd.ws<__half>(x.off);
+  }
+  bd.drop(x);
+  pl->total_bytes = bd.arena_base + bd.arena.peak;
+  pl->flops = 0;
+  for (auto& op : pl->ops) pl->flops += op.flops;
+  return 0;
+}
+
+Plan* get_plan(cdc_engine* e, int B, int H, int W, void* ws, int* rc) {
+  *rc = 0;
+  if (e->dry) { *rc = fail(e, CDC_ERR_STATE, "planning-only engine (device=-1) cannot compute: there is no CPU path"); return nullptr; }
+  if (!e->finalized) { *rc = fail(e, CDC_ERR_STATE, "engine not finalized"); return nullptr; }
+  if (B < 1 || H < 32 || W < 32 || (H % 32) || (W % 32)) {
+    *rc = fail(e, CDC_ERR_INVALID, "unsupported shape B=%d H=%d W=%d (need B>=1, H,W multiples of 32)", B, H, W);
+    return nullptr;
+  }
+  if ((H >> (e->cfg.n_levels - 1)) < 1) { *rc = fail(e, CDC_ERR_INVALID, "image too small"); return nullptr; }
+  auto key = std::make_tuple(B, H, W, (uintptr_t)ws);
+  auto it = e->plans.find(key);
+  if (it != e->plans.end()) return it->second.get();
+  if (e->plans.size() > 16) {
+    for (auto& kv : e->plans) if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+    e->plans.clear();
+    e->last_plan = nullptr;
+  }
+  std::unique_ptr<Plan> pl(new Plan());
+  *rc = build_plan(e, pl.get(), B, H, W, (uint8_t*)ws);
+  if (*rc) return nullptr;
+  Plan* raw = pl.get();
+  e->plans[key] = std::move(pl);
+  return raw;
+}
+
+struct RunArgs {
+  const float* x = nullptr;     // network input (fp32 NCHW)
+  const float* time = nullptr;  // [B] or null (use schedule table)
+  float* out = nullptr;         // mode 0
+  float* x_inout = nullptr;     // mode 1
+  const float* z = nullptr;
+  int mode = 0, pred = 0, clip = 0;
+  bool advance = false;
+};
+
+int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
+  const cdc_config& cfg = e->cfg;
+  const int B = pl->B, H = pl->H, W = pl->W;
+  for (size_t i = 0; i < pl->ops.size(); ++i) {
+    const Op& op = pl->ops[i];
+    switch (op.kind) {
+      case OP_TIME: {
+        const size_t sm = (size_t)5 * cfg.dim * 4;
+        time_mlp_kernel<<<B, 256, sm, st>>>(a.time, a.time ? nullptr : e->d_table, e->d_step,
+                                            dptr<float>(e, e->t_w1), dptr<float>(e, e->t_b1), dptr<float>(e, e->t_w2),
+                                            dptr<float>(e, e->t_b2), dptr<float>(e, e->t_wcat),
+                                            dptr<float>(e, e->t_bcat), cfg.dim, e->R,
+                                            reinterpret_cast<float*>(pl->ws + pl->shifts_off));
+        break;
+      }
+      case OP_PACK: {
+        const long long total = (long long)B * H * W * 8;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        const float* c0 = e->fold_ctx0 ? reinterpret_cast<const float*>(pl->ws + pl->ctx_off[0]) : nullptr;
+        pack_input_kernel<<<blocks, 256, 0, st>>>(a.x, cfg.channels, c0, e->fold_ctx0 ? cfg.context_channels : 0, B, H,
+                                                  W, const_cast<__half*>(op.dbg));
+        break;
+      }
+      case OP_CONV: {
+        cudaError_t err = launch_igemm(op, st);
+        if (err != cudaSuccess)
+          return fail(e, CDC_ERR_CUDA, "conv launch '%s' (bm=%d bn=%d epi=%d): %s", op.name.c_str(), op.bm, op.bn,
+                      op.epi, cudaGetErrorString(err));
+        break;
+      }
+      case OP_ATTN_CTX:
+        attn_ctx_kernel<<<op.grid, 256, AttnCtxSmem::kBytes, st>>>(op.actx);
+        break;
+      case OP_COMBINE:
+        attn_combine_kernel<<<op.grid, 128, 0, st>>>(op.comb.pc, op.comb.pm, op.comb.ps, op.comb.C, op.comb.nchunks,
+                                                     op.comb.out);
+        break;
+      case OP_SGEMM:
+        sgemm_tn_kernel<<<op.grid, 256, 0, st>>>(op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N, op.sg.K, op.sg.sA,
+                                                 op.sg.sB, op.sg.sC);
+        break;
+      case OP_FINISH:
+        attn_finish_kernel<<<op.grid, 128, 0, st>>>(op.fin.Mf, op.fin.g, op.fin.bln, op.fin.bout, op.fin.C, op.fin.Mg,
+                                                    op.fin.um, op.fin.cm);
+        break;
+      case OP_FINAL: {
+        FinalParams fp{};
+        fp.in = op.conv.seg[0].src;
+        fp.ln_g = dptr<float>(e, e->f_g);
+        fp.ln_b = dptr<float>(e, e->f_b);
+        fp.Wf = dptr<__half>(e, e->f_w);
+        fp.bias = dptr<float>(e, e->f_bias);
+        fp.B = B; fp.H = H; fp.W = W; fp.channels = cfg.channels;
+        fp.mode = a.mode;
+        fp.out = a.out;
+        fp.x = a.x_inout;
+        fp.z = a.z;
+        fp.table = e->d_table;
+        fp.step_ptr = e->d_step;
+        fp.variant = cfg.variant;
+        fp.pred_mode = a.pred;
+        fp.clip_mode = a.clip;
+        final_conv_kernel<<<dim3(W / 16, H / 16, B), 256, kFinalSmemBytes, st>>>(fp);
+        break;
+      }
+      default:
+        break;
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+      return fail(e, CDC_ERR_CUDA, "launch of op %zu '%s' failed: %s", i, op.name.c_str(), cudaGetErrorString(err));
+  }
+  if (a.advance) {
+    advance_step_kernel<<<1, 32, 0, st>>>(e->d_step);
+  }
+  e->last_plan = pl;
+  return 0;
+}
+
+__global__ void set_int_kernel(int* p, int v) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
+}
+
+int convert_context(cdc_engine* e, Plan* pl, const float* const* ctx, int n_ctx, cudaStream_t st) {
+  const cdc_config& cfg = e->cfg;
+  if (n_ctx != cfg.n_context) return fail(e, CDC_ERR_INVALID, "expected %d context tensors, got %d", cfg.n_context, n_ctx);
+  for (int l = 0; l < n_ctx; ++l) {
+    const int c = e->cdims[l], h = pl->H >> l, w = pl->W >> l;
+    if (!ctx[l]) return fail(e, CDC_ERR_INVALID, "context[%d] is null", l);
+    if (l == 0 && e->fold_ctx0) {
+      CUDA_TRY(e, cudaMemcpyAsync(pl->ws + pl->ctx_off[0], ctx[0], (size_t)pl->B * c * h * w * 4,
+                                  cudaMemcpyDeviceToDevice, st));
+    } else {
+      dim3 grid((h * w + 31) / 32, (c + 31) / 32, pl->B);
+      nchw_to_nhwc_half_kernel<<<grid, 256, 0, st>>>(ctx[l], c, h * w, reinterpret_cast<__half*>(pl->ws + pl->ctx_off[l]));
+      CUDA_TRY(e, cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int cdc_abi_version(void) { return CDC_ABI_VERSION; }
+
+const char* cdc_last_error(const cdc_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
+  if (!cfg || !out) return fail(nullptr, CDC_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != CDC_ABI_VERSION) return fail(nullptr, CDC_ERR_INVALID, "ABI version mismatch");
+  if (cfg->variant != CDC_VARIANT_EPS && cfg->variant != CDC_VARIANT_X)
+    return fail(nullptr, CDC_ERR_INVALID, "unknown variant %d", cfg->variant);
+  if (cfg->dim != 64)
+    return fail(nullptr, CDC_ERR_UNSUPPORTED, "dim=%d unsupported: the kernel family is specialised for dim=64", cfg->dim);
+  if (cfg->n_levels < 2 || cfg->n_levels > CDC_MAX_LEVELS) return fail(nullptr, CDC_ERR_UNSUPPORTED, "n_levels=%d unsupported", cfg->n_levels);
+  if (cfg->n_context < 0 || cfg->n_context > cfg->n_levels - 1)
+    return fail(nullptr, CDC_ERR_UNSUPPORTED, "n_context=%d unsupported", cfg->n_context);
+  if (cfg->channels < 1 || cfg->channels > 8) return fail(nullptr, CDC_ERR_UNSUPPORTED, "channels=%d unsupported", cfg->channels);
+  for (int i = 0; i < cfg->n_levels; ++i)
+    if (cfg->dim_mults[i] < 1 || cfg->dim_mults[i] > 6)
+      return fail(nullptr, CDC_ERR_UNSUPPORTED, "dim_mults[%d]=%d unsupported (1..6)", i, cfg->dim_mults[i]);
+  for (int i = 0; i < cfg->n_context; ++i)
+    if (cfg->context_dim_mults[i] < 1 || cfg->context_dim_mults[i] > 6)
+      return fail(nullptr, CDC_ERR_UNSUPPORTED, "context_dim_mults[%d] unsupported", i);
+  std::unique_ptr<cdc_engine> e(new cdc_engine());
+  e->cfg = *cfg;
+  e->device = device;
+  e->dims.push_back(cfg->channels);
+  for (int i = 0; i < cfg->n_levels; ++i) e->dims.push_back(cfg->dim * cfg->dim_mults[i]);
+  e->cdims.push_back(cfg->context_channels);
+  for (int i = 0; i + 1 < cfg->n_context; ++i) e->cdims.push_back(cfg->dim * cfg->context_dim_mults[i]);
+  if (cfg->n_context > 0) {
+    if (cfg->context_channels % 64 == 0 && cfg->context_channels <= 384) e->fold_ctx0 = false;
+    else if (cfg->channels + cfg->context_channels <= 8) e->fold_ctx0 = true;
+    else return fail(nullptr, CDC_ERR_UNSUPPORTED, "context_channels=%d unsupported (multiple of 64, or channels+context_channels<=8)", cfg->context_channels);
+  }
+  if (device == -1) {
+    // host-only planning engine: validates weights, sizes workspaces, counts launches/FLOPs; cannot compute.
+    e->dry = true;
+    *out = e.release();
+    return CDC_OK;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, CDC_ERR_CUDA, "no CUDA device: the CDC engine has no CPU path");
+  if (device < 0 || device >= ndev) return fail(nullptr, CDC_ERR_INVALID, "device %d out of range", device);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, CDC_ERR_CUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) return fail(nullptr, CDC_ERR_UNSUPPORTED, "device sm_%d%d: this build targets sm_100a only", prop.major, prop.minor);
+  if (cudaMalloc(&e->d_step, sizeof(int)) != cudaSuccess) return fail(nullptr, CDC_ERR_CUDA, "cudaMalloc failed");
+  cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
+  cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
+  *out = e.release();
+  return CDC_OK;
+}
+
+void cdc_engine_destroy(cdc_engine* e) {
+  if (!e) return;
+  if (e->dry) { delete e; return; }
+  cudaSetDevice(e->device);
+  for (auto& kv : e->plans) if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+  if (e->dblob) cudaFree(e->dblob);
+  if (e->d_table) cudaFree(e->d_table);
+  if (e->d_step) cudaFree(e->d_step);
+  delete e;
+}
+
+int cdc_engine_set_weight(cdc_engine* e, const char* key, const float* host_ptr, const int64_t* shape, int ndim) {
+  if (!e || !key || !host_ptr || !shape || ndim < 1 || ndim > 8) return fail(e, CDC_ERR_INVALID, "bad set_weight argument");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(host_ptr, host_ptr + n);
+  e->weights[key] = std::move(t);
+  e->finalized = false;
+  return CDC_OK;
+}
+
+int cdc_engine_finalize(cdc_engine* e) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!e->dry) cudaSetDevice(e->device);
+  const cdc_config& cfg = e->cfg;
+  const int L = cfg.n_levels, dim = cfg.dim;
+  e->blob.host.clear();
+  e->downs.assign(L, Level());
+  e->ups.assign(L - 1, Level());
+  std::vector<float> wcat, bcat;
+  int rc = 0;
+  // time MLP
+  {
+    const HostTensor* w1 = find(e, "time_mlp.0.weight", {4 * dim, 1}, &rc); if (!w1) return rc;
+    const HostTensor* b1 = find(e, "time_mlp.0.bias", {4 * dim}, &rc); if (!b1) return rc;
+    const HostTensor* w2 = find(e, "time_mlp.2.weight", {dim, 4 * dim}, &rc); if (!w2) return rc;
+    const HostTensor* b2 = find(e, "time_mlp.2.bias", {dim}, &rc); if (!b2) return rc;
+    e->t_w1 = put_f32(e, w1->data.data(), w1->data.size());
+    e->t_b1 = put_f32(e, b1->data.data(), b1->data.size());
+    e->t_w2 = put_f32(e, w2->data.data(), w2->data.size());
+    e->t_b2 = put_f32(e, b2->data.data(), b2->data.size());
+  }
+  for (int l = 0; l < L; ++l) {
+    Level& lv = e->downs[l];
+    const bool last = l >= L - 1;
+    const bool has_ctx = !last && l < cfg.n_context;
+    const int cx = e->dims[l], cc = has_ctx ? e->cdims[l] : 0;
+    const int cin = cx + cc, cout = e->dims[l + 1];
+    lv.cin = cin; lv.cout = cout;
+    const std::string p = "downs." + std::to_string(l) + ".";
+    std::vector<SegSpec> s1, sr;
+    if (l == 0) {
+      const int folded = (has_ctx && e->fold_ctx0) ? cc : 0;
+      s1.push_back({64, 7, 1, 1, 0, cx + folded});
+      sr.push_back({64, 1, 1, 2, 0, cx + folded});
+      if (has_ctx && !e->fold_ctx0) {
+        s1.push_back({cc, 7, 7, 0, cx, 0});
+        sr.push_back({cc, 1, 1, 0, cx, 0});
+      }
+    } else {
+      s1.push_back({cx, 3, 3, 0, 0, 0});
+      sr.push_back({cx, 1, 1, 0, 0, 0});
+      if (has_ctx) {
+        s1.push_back({cc, 3, 3, 0, cx, 0});
+        sr.push_back({cc, 1, 1, 0, cx, 0});
+      }
+    }
+    if ((rc = pack_resnet(e, p + "0.", cin, cout, l == 0 ? 7 : 3, s1, sr, &lv.rb0, &wcat, &bcat))) return rc;
+    std::vector<SegSpec> s2 = {{cout, 3, 3, 0, 0, 0}}, sr2 = {{cout, 1, 1, 0, 0, 0}};
+    if ((rc = pack_resnet(e, p + "1.", cout, cout, 3, s2, sr2, &lv.rb1, &wcat, &bcat))) return rc;
+    if ((rc = pack_attn(e, p + "2.", cout, &lv.attn))) return rc;
+    lv.has_resample = !last;
+    if (!last) {
+      std::vector<SegSpec> sd = {{cout, 3, 3, 0, 0, 0}};
+      if ((rc = pack_conv(e, p + "3.conv", cout, cout, 3, 3, sd, true, &lv.resample))) return rc;
+    }
+  }
+  {
+    const int c = e->dims[L];
+    std::vector<SegSpec> s = {{c, 3, 3, 0, 0, 0}}, sr = {{c, 1, 1, 0, 0, 0}};
+    if ((rc = pack_resnet(e, "mid_block1.", c, c, 3, s, sr, &e->mid1, &wcat, &bcat))) return rc;
+    if ((rc = pack_attn(e, "mid_attn.", c, &e->mid_attn))) return rc;
+    if ((rc = pack_resnet(e, "mid_block2.", c, c, 3, s, sr, &e->mid2, &wcat, &bcat))) return rc;
+  }
+  for (int l = 0; l < L - 1; ++l) {
+    Level& lv = e->ups[l];
+    const int dim_in = e->dims[L - 1 - l], dim_out = e->dims[L - l];
+    lv.cin = 2 * dim_out; lv.cout = dim_in;
+    const std::string p = "ups." + std::to_string(l) + ".";
+    std::vector<SegSpec> s1 = {{dim_out, 3, 3, 0, 0, 0}, {dim_out, 3, 3, 0, dim_out, 0}};
+    std::vector<SegSpec> sr = {{dim_out, 1, 1, 0, 0, 0}, {dim_out, 1, 1, 0, dim_out, 0}};
+    if ((rc = pack_resnet(e, p + "0.", 2 * dim_out, dim_in, 3, s1, sr, &lv.rb0, &wcat, &bcat))) return rc;
+    std::vector<SegSpec> s2 = {{dim_in, 3, 3, 0, 0, 0}}, sr2 = {{dim_in, 1, 1, 0, 0, 0}};
+    if ((rc = pack_resnet(e, p + "1.", dim_in, dim_in, 3, s2, sr2, &lv.rb1, &wcat, &bcat))) return rc;
+    if ((rc = pack_attn(e, p + "2.", dim_in, &lv.attn))) return rc;
+    lv.has_resample = true;
+    if ((rc = pack_convT(e, p + "3.conv", dim_in, dim_in, &lv.resample))) return rc;
+  }
+  // final LayerNorm + 7x7 conv
+  {
+    if ((rc = pack_ln(e, "final_conv.0", dim, &e->f_g, &e->f_b))) return rc;
+    const HostTensor* w = find(e, "final_conv.1.weight", {cfg.channels, dim, 7, 7}, &rc); if (!w) return rc;
+    const HostTensor* b = find(e, "final_conv.1.bias", {cfg.channels}, &rc); if (!b) return rc;
+    std::vector<__half> wf((size_t)8 * kFinalWStride, __float2half(0.f));
+    for (int n = 0; n < cfg.channels; ++n)
+      for (int c = 0; c < 64; ++c)
+        for (int ky = 0; ky < 7; ++ky)
+          for (int kx = 0; kx < 7; ++kx)
+            wf[(size_t)n * kFinalWStride + (ky * 7 + kx) * 64 + c] =
+                __float2half_rn(w->data[(((size_t)n * dim + c) * 7 + ky) * 7 + kx]);
+    e->f_w = e->blob.reserve(wf.size() * 2);
+    memcpy(e->blob.at<__half>(e->f_w), wf.data(), wf.size() * 2);
+    e->f_bias = put_f32(e, b->data.data(), cfg.channels);
+  }
+  e->R = (int)bcat.size();
+  e->t_wcat = put_f32(e, wcat.data(), wcat.size());
+  e->t_bcat = put_f32(e, bcat.data(), bcat.size());
+  if (e->dry) {
+    e->plans.clear();
+    e->last_plan = nullptr;
+    e->finalized = true;
+    return CDC_OK;
+  }
+  // upload
+  if (e->dblob && e->dblob_bytes < e->blob.host.size()) { cudaFree(e->dblob); e->dblob = nullptr; }
+  if (!e->dblob) {
+    CUDA_TRY(e, cudaMalloc(&e->dblob, e->blob.host.size()));
+    e->dblob_bytes = e->blob.host.size();
+  }
+  CUDA_TRY(e, cudaMemcpy(e->dblob, e->blob.host.data(), e->blob.host.size(), cudaMemcpyHostToDevice));
+  for (auto& kv : e->plans) if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+  e->plans.clear();
+  e->last_plan = nullptr;
+  e->ctx_set = false;
+  e->finalized = true;
+  return CDC_OK;
+}
+
+int64_t cdc_engine_workspace_bytes(cdc_engine* e, int B, int H, int W) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!e->finalized) return fail(e, CDC_ERR_STATE, "engine not finalized");
+  if (B < 1 || H < 32 || W < 32 || (H % 32) || (W % 32))
+    return fail(e, CDC_ERR_INVALID, "unsupported shape B=%d H=%d W=%d (need H,W multiples of 32)", B, H, W);
+  Plan pl;
+  int rc = build_plan(e, &pl, B, H, W, nullptr);
+  if (rc) return rc;
+  return (int64_t)pl.total_bytes;
+}
+
+static int check_ws(cdc_engine* e, Plan* pl, int64_t workspace_bytes) {
+  if ((int64_t)pl->total_bytes > workspace_bytes)
+    return fail(e, CDC_ERR_INVALID, "workspace too small: need %zu bytes, got %lld", pl->total_bytes, (long long)workspace_bytes);
+  return 0;
+}
+
+int cdc_unet_forward(cdc_engine* e, const float* x, const float* time, const float* const* ctx, int n_ctx, float* out,
+                     int B, int H, int W, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!x || !time || !out || !workspace) return fail(e, CDC_ERR_INVALID, "null pointer argument");
+  cudaSetDevice(e->device);
+  int rc;
+  Plan* pl = get_plan(e, B, H, W, workspace, &rc);
+  if (!pl) return rc;
+  if ((rc = check_ws(e, pl, workspace_bytes))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = convert_context(e, pl, ctx, n_ctx, st))) return rc;
+  e->ctx_set = false;  // forward() owns the persistent region for this call only
+  RunArgs a;
+  a.x = x; a.time = time; a.out = out; a.mode = 0;
+  return run_plan(e, pl, a, st);
+}
+
+int cdc_set_context(cdc_engine* e, const float* const* ctx, int n_ctx, int B, int H, int W, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!workspace) return fail(e, CDC_ERR_INVALID, "null workspace");
+  cudaSetDevice(e->device);
+  int rc;
+  Plan* pl = get_plan(e, B, H, W, workspace, &rc);
+  if (!pl) return rc;
+  if ((rc = check_ws(e, pl, workspace_bytes))) return rc;
+  if ((rc = convert_context(e, pl, ctx, n_ctx, (cudaStream_t)stream))) return rc;
+  e->ctx_set = true;
+  e->ctx_B = B; e->ctx_H = H; e->ctx_W = W; e->ctx_ws = (uintptr_t)workspace;
+  return CDC_OK;
+}
+
+int cdc_set_schedule(cdc_engine* e, const cdc_step_coef* host_coefs, int S, void* stream) {
+  if (!e || !host_coefs || S < 1) return fail(e, CDC_ERR_INVALID, "bad schedule");
+  if (e->dry) return fail(e, CDC_ERR_STATE, "planning-only engine (device=-1) cannot compute: there is no CPU path");
+  cudaSetDevice(e->device);
+  if (S > e->table_cap) {
+    if (e->d_table) cudaFree(e->d_table);
+    e->d_table = nullptr;
+    CUDA_TRY(e, cudaMalloc(&e->d_table, (size_t)S * sizeof(cdc_step_coef)));
+    e->table_cap = S;
+    // graphs captured the old table pointer
+    for (auto& kv : e->plans) if (kv.second->graph) { cudaGraphExecDestroy(kv.second->graph); kv.second->graph = nullptr; }
+  }
+  // synchronous copy from pageable host memory: the caller's buffer may be freed right after return
+  CUDA_TRY(e, cudaStreamSynchronize((cudaStream_t)stream));
+  CUDA_TRY(e, cudaMemcpy(e->d_table, host_coefs, (size_t)S * sizeof(cdc_step_coef), cudaMemcpyHostToDevice));
+  e->S = S;
+  return CDC_OK;
+}
+
+static int sampler_prologue(cdc_engine* e, int B, int H, int W, void* workspace, int64_t workspace_bytes, int pred_mode,
+                            int clip_mode, Plan** out) {
+  if (!e->ctx_set || e->ctx_B != B || e->ctx_H != H || e->ctx_W != W || e->ctx_ws != (uintptr_t)workspace)
+    return fail(e, CDC_ERR_STATE, "cdc_set_context must be called first with the same shape and workspace");
+  if (e->S < 1) return fail(e, CDC_ERR_STATE, "cdc_set_schedule must be called first");
+  if (e->cfg.variant == CDC_VARIANT_EPS && pred_mode != CDC_PRED_NOISE)
+    return fail(e, CDC_ERR_UNSUPPORTED, "eps variant supports pred_mode 'noise' only");
+  if (pred_mode < 0 || pred_mode > 2 || clip_mode < 0 || clip_mode > 2) return fail(e, CDC_ERR_INVALID, "bad pred/clip mode");
+  int rc;
+  Plan* pl = get_plan(e, B, H, W, workspace, &rc);
+  if (!pl) return rc;
+  if ((rc = check_ws(e, pl, workspace_bytes))) return rc;
+  *out = pl;
+  return 0;
+}
+
+int cdc_ddim_step(cdc_engine* e, float* x_inout, int i, const float* z, int pred_mode, int clip_mode, int B, int H,
+                  int W, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!x_inout) return fail(e, CDC_ERR_INVALID, "null x");
+  cudaSetDevice(e->device);
+  Plan* pl;
+  int rc = sampler_prologue(e, B, H, W, workspace, workspace_bytes, pred_mode, clip_mode, &pl);
+  if (rc) return rc;
+  if (i < 0 || i >= e->S) return fail(e, CDC_ERR_INVALID, "step index %d outside schedule of %d", i, e->S);
+  cudaStream_t st = (cudaStream_t)stream;
+  set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i);
+  RunArgs a;
+  a.x = x_inout; a.x_inout = x_inout; a.z = z; a.mode = 1; a.pred = pred_mode; a.clip = clip_mode;
+  return run_plan(e, pl, a, st);
+}
+
+int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int pred_mode, int clip_mode, int B, int H,
+                    int W, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!x_inout) return fail(e, CDC_ERR_INVALID, "null x");
+  cudaSetDevice(e->device);
+  Plan* pl;
+  int rc = sampler_prologue(e, B, H, W, workspace, workspace_bytes, pred_mode, clip_mode, &pl);
+  if (rc) return rc;
+  if (i_first >= e->S || i_last < 0 || i_last > i_first) return fail(e, CDC_ERR_INVALID, "bad step range %d..%d (S=%d)", i_first, i_last, e->S);
+  cudaStream_t st = (cudaStream_t)stream;
+  int i_start = i_first;
+  if (!pl->graph || pl->graph_x != x_inout || pl->graph_pred != pred_mode || pl->graph_clip != clip_mode) {
+    if (pl->graph) { cudaGraphExecDestroy(pl->graph); pl->graph = nullptr; }
+    RunArgs a;
+    a.x = x_inout; a.x_inout = x_inout; a.z = nullptr; a.mode = 1; a.pred = pred_mode; a.clip = clip_mode; a.advance = true;
+    // The first step runs eagerly: it is real work AND it forces every kernel's module load /
+    // attribute setup to happen before stream capture starts.
+    set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
+    if ((rc = run_plan(e, pl, a, st))) return rc;
+    i_start = i_first - 1;
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = run_plan(e, pl, a, st);
+    cudaError_t err = cudaStreamEndCapture(st, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (err != cudaSuccess) return fail(e, CDC_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err));
+    err = cudaGraphInstantiate(&pl->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (err != cudaSuccess) { pl->graph = nullptr; return fail(e, CDC_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(err)); }
+    pl->graph_x = x_inout; pl->graph_pred = pred_mode; pl->graph_clip = clip_mode;
+  } else {
+    set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
+  }
+  for (int i = i_start; i >= i_last; --i) CUDA_TRY(e, cudaGraphLaunch(pl->graph, st));
+  e->last_plan = pl;
+  return CDC_OK;
+}
+
+int cdc_engine_launches_per_forward(cdc_engine* e, int B, int H, int W) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!e->finalized) return fail(e, CDC_ERR_STATE, "engine not finalized");
+  Plan pl;
+  int rc = build_plan(e, &pl, B, H, W, nullptr);
+  if (rc) return rc;
+  return (int)pl.ops.size();
+}
+int cdc_engine_launches_per_step(cdc_engine* e, int B, int H, int W) {
+  int n = cdc_engine_launches_per_forward(e, B, H, W);
+  return n < 0 ? n : n + 1;  // + advance_step
+}
+double cdc_engine_flops_per_forward(cdc_engine* e, int B, int H, int W) {
+  if (!e || !e->finalized) return -1.0;
+  Plan pl;
+  if (build_plan(e, &pl, B, H, W, nullptr)) return -1.0;
+  return pl.flops;
+}
+int cdc_engine_num_ops(cdc_engine* e, int B, int H, int W) { return cdc_engine_launches_per_forward(e, B, H, W); }
+
+const char* cdc_engine_op_name(cdc_engine* e, int op_index) {
+  if (!e || !e->last_plan || op_index < 0 || op_index >= (int)e->last_plan->ops.size()) return "";
+  return e->last_plan->ops[op_index].name.c_str();
+}
+
+int64_t cdc_engine_debug_read(cdc_engine* e, int op_index, float* host_out, int64_t capacity, int* C, int* H, int* W) {
+  if (!e || !e->last_plan) return fail(e, CDC_ERR_STATE, "no forward has run");
+  Plan* pl = e->last_plan;
+  if (op_index < 0 || op_index >= (int)pl->ops.size()) return fail(e, CDC_ERR_INVALID, "op index out of range");
+  const Op& op = pl->ops[op_index];
+  if (!op.dbg) return 0;
+  const int64_t n = (int64_t)pl->B * op.dH * op.dW * op.dC;
+  if (C) *C = op.dC;
+  if (H) *H = op.dH;
+  if (W) *W = op.dW;
+  if (!host_out) return n;
+  if (capacity < n) return fail(e, CDC_ERR_INVALID, "debug buffer too small");
+  cudaSetDevice(e->device);
+  std::vector<__half> tmp((size_t)n);
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  CUDA_TRY(e, cudaMemcpy(tmp.data(), op.dbg, (size_t)n * 2, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) host_out[i] = __half2float(tmp[(size_t)i]);
+  return n;
+}
+
+int cdc_engine_set_debug(cdc_engine* e, int no_reuse) {
+  if (!e) return CDC_ERR_INVALID;
+  e->debug_no_reuse = no_reuse != 0;
+  for (auto& kv : e->plans) if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+  e->plans.clear();
+  e->last_plan = nullptr;
+  e->ctx_set = false;
+  return CDC_OK;
+}
+
+int cdc_engine_set_mainloop(cdc_engine* e, int kind) {
+  if (!e) return CDC_ERR_INVALID;
+  if (kind != 0) return fail(e, CDC_ERR_UNSUPPORTED, "mainloop %d not built", kind);
+  e->mainloop = kind;
+  return CDC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+// Layout/packing kernels, the timestep MLP, and the fused final LayerNorm + 7x7 conv + DDIM update.
+#pragma once
+#include "../../include/cdc_b200.h"
+#include "common.cuh"
+
+namespace cdc {
+
+// ------------------------------------------------------------------------------------------------
+// x_t (fp32 NCHW, `cx` channels) [+ a small fp32 NCHW context with `cc` channels, cx+cc <= 8]
+//   -> X0 [B,H,W,64] fp16 with channel kx*8+c = value at (y, x+kx-3): the horizontal taps of the first
+//   7x7 convolution (unet.py:61 / network_components.py:87) folded into K, so that conv runs as 7
+//   vertical taps of 64 channels.  Slot kx=7 and channels >= cx+cc are zero.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_input_kernel(const float* __restrict__ x, int cx, const float* __restrict__ ctx, int cc,
+                                  int B, int H, int W, __half* __restrict__ out) {
+  const long long total = (long long)B * H * W * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int xx = (int)(pix % W);
+    const long long t = pix / W;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    const int sx = xx + kx - 3;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    if (kx < 7 && sx >= 0 && sx < W) {
+      for (int c = 0; c < cx; ++c) v[c] = x[(((size_t)b * cx + c) * H + yy) * W + sx];
+      for (int c = 0; c < cc; ++c) v[cx + c] = ctx[(((size_t)b * cc + c) * H + yy) * W + sx];
+    }
+    uint4 o;
+    o.x = pack_half2(v[0], v[1]);
+    o.y = pack_half2(v[2], v[3]);
+    o.z = pack_half2(v[4], v[5]);
+    o.w = pack_half2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
+  }
+}
+
+// fp32 NCHW [B,C,HW] -> fp16 NHWC [B,HW,C]   (context maps, once per decode)
+__global__ void nchw_to_nhwc_half_kernel(const float* __restrict__ in, int C, int HW, __half* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, pp = p0 + tx;
+    tile[j][tx] = (c < C && pp < HW) ? in[((size_t)b * C + c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int pp = p0 + j, c = c0 + tx;
+    if (c < C && pp < HW) out[((size_t)b * HW + pp) * C + c] = __float2half_rn(tile[tx][j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Timestep path: temb = W2 gelu_erf(W1 t + b1) + b2 (unet.py:40), then for every ResnetBlock
+// shift = Wk leaky_relu_0.2(temb) + bk (network_components.py:97-101,110-111).  One CTA per image;
+// all blocks' Linear layers are concatenated row-wise ([R][dim]).
+// ------------------------------------------------------------------------------------------------
+__global__ void time_mlp_kernel(const float* __restrict__ time, const cdc_step_coef* __restrict__ table,
+                                const int* __restrict__ step_ptr, const float* __restrict__ W1,
+                                const float* __restrict__ b1, const float* __restrict__ W2,
+                                const float* __restrict__ b2, const float* __restrict__ Wcat,
+                                const float* __restrict__ bcat, int dim, int R, float* __restrict__ shifts) {
+  extern __shared__ float sm[];
+  float* hid = sm;            // [4*dim]
+  float* act = sm + 4 * dim;  // [dim]
+  const int b = blockIdx.x;
+  const float t = table ? table[*step_ptr].unet_time : time[b];
+  for (int j = threadIdx.x; j < 4 * dim; j += blockDim.x) {
+    const float v = W1[j] * t + b1[j];
+    hid[j] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+    float a = b2[j];
+    const float* w = W2 + (size_t)j * 4 * dim;
+    for (int k = 0; k < 4 * dim; ++k) a = fmaf(w[k], hid[k], a);
+    act[j] = a > 0.f ? a : 0.2f * a;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float a = bcat[r];
+    const float* w = Wcat + (size_t)r * dim;
+    for (int k = 0; k < dim; ++k) a = fmaf(w[k], act[k], a);
+    shifts[(size_t)b * R + r] = a;
+  }
+}
+
+__global__ void advance_step_kernel(int* step_ptr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *step_ptr -= 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// final_conv = LayerNorm(64) -> Conv2d(64, channels<=8, 7, pad 3) (unet.py:93) fused with the DDIM
+// update (epsilonparam/modules/denoising_diffusion.py:137-152; xparam/...:152-174).
+// CTA = 16x16 output pixels; the 22x22x64 halo is LayerNorm-ed once into shared memory (zeros
+// outside the image: padding applies to the LayerNorm output), then M=256,N=8,K=49*64 on mma.sync.
+// ------------------------------------------------------------------------------------------------
+struct FinalParams {
+  const __half* in;     // [B,H,W,64] fp16
+  const float* ln_g;    // [64]
+  const float* ln_b;
+  const __half* Wf;     // [8][kFinalWStride] fp16, K index = (ky*7+kx)*64 + c, rows >= channels are zero
+  const float* bias;    // [channels]
+  int B, H, W, channels;
+  // mode 0: out = network output (Unet.forward).  mode 1: in-place DDIM update of x.
+  int mode;
+  float* out;           // mode 0: [B,channels,H,W] fp32
+  float* x;             // mode 1: x_t in / x_{t-1} out, fp32 NCHW
+  const float* z;       // optional noise
+  const cdc_step_coef* table;
+  const int* step_ptr;
+  int variant, pred_mode, clip_mode;
+};
+
+constexpr int kFinalWStride = 49 * 64 + 8;
+constexpr int kFinalHalo = 22;
+constexpr int kFinalSmemBytes = kFinalHalo * kFinalHalo * 128 + 8 * kFinalWStride * 2;
+
+__global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sIn = smem;
+  __half* sW = reinterpret_cast<__half*>(smem + kFinalHalo * kFinalHalo * 128);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z, y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
+
+  // weights -> smem (16B copies; 8*3144*2 bytes)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.Wf);
+    uint4* dst = reinterpret_cast<uint4*>(sW);
+    for (int i = tid; i < 8 * kFinalWStride * 2 / 16; i += 256) dst[i] = src[i];
+  }
+  // halo load + LayerNorm: 8 threads per pixel, 8 channels each
+  {
+    const int j = tid & 7;
+    float g[8], bb[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      g[c] = p.ln_g[j * 8 + c];
+      bb[c] = p.ln_b[j * 8 + c];
+    }
+    for (int hp0 = 0; hp0 < kFinalHalo * kFinalHalo; hp0 += 32) {
+      const int hp = hp0 + (tid >> 3);
+      const int hy = hp / kFinalHalo, hx = hp - hy * kFinalHalo;
+      const int yy = y0 + hy - 3, xx = x0 + hx - 3;
+      const bool inb = hp < kFinalHalo * kFinalHalo && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      float v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = 0.f;
+      if (inb) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p.in + (((size_t)b * p.H + yy) * p.W + xx) * 64 + j * 8);
+        float2 f;
+        f = unpack_half2(raw.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_half2(raw.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_half2(raw.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_half2(raw.w); v[6] = f.x; v[7] = f.y;
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) s += v[c];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      const float mean = s * (1.f / 64.f);
+      float q = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float d = v[c] - mean;
+        q += d * d;
+      }
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      q += __shfl_xor_sync(0xffffffffu, q, 4);
+      const float rstd = 1.f / sqrtf(q * (1.f / 64.f) + 1e-5f);
+      if (hp < kFinalHalo * kFinalHalo) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (inb) {
+          float y[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) y[c] = (v[c] - mean) * rstd * g[c] + bb[c];
+          o.x = pack_half2(y[0], y[1]);
+          o.y = pack_half2(y[2], y[3]);
+          o.z = pack_half2(y[4], y[5]);
+          o.w = pack_half2(y[6], y[7]);
+        }
+        *reinterpret_cast<uint4*>(sIn + swz128(hp, j)) = o;
+      }
+    }
+  }
+  __syncthreads();
+
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
+  const uint32_t sIn32 = smem_u32(sIn), sW32 = smem_u32(sW);
+  for (int tap = 0; tap < 49; ++tap) {
+    const int ky = tap / 7, kx = tap - ky * 7;
+#pragma unroll
+    for (int ks = 0; ks < 4; ks += 2) {
+      uint32_t bf[4];
+      ldmatrix_x4(bf, sW32 + ((lane & 7) * kFinalWStride + tap * 64 + ks * 16 + (lane >> 3) * 8) * 2);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int ty = warp * 2 + mt;
+        const int hp = (ty + ky) * kFinalHalo + (lane & 15) + kx;
+        uint32_t a0[4], a1[4];
+        ldmatrix_x4(a0, sIn32 + swz128(hp, ks * 2 + (lane >> 4)));
+        ldmatrix_x4(a1, sIn32 + swz128(hp, (ks + 1) * 2 + (lane >> 4)));
+        mma_16816(acc[mt], a0, bf[0], bf[1]);
+        mma_16816(acc[mt], a1, bf[2], bf[3]);
+      }
+    }
+  }
+
+  // epilogue: lane holds (pixel tx = lane>>2 (+8), channels n = 2*(lane&3), +1)
+  const int n_base = (lane & 3) * 2;
+  cdc_step_coef cf = {};
+  if (p.mode == 1) cf = p.table[*p.step_ptr];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = n_base + e;
+        if (n >= p.channels) continue;
+        const int yy = y0 + warp * 2 + mt, xx = x0 + (lane >> 2) + h * 8;
+        if (yy >= p.H || xx >= p.W) continue;
+        const float f = acc[mt][2 * h + e] + p.bias[n];
+        const size_t idx = (((size_t)b * p.channels + n) * p.H + yy) * p.W + xx;
+        if (p.mode == 0) {
+          p.out[idx] = f;
+          continue;
+        }
+        const float xt = p.x[idx];
+        float x0v, noise;
+        const bool clip = p.clip_mode == CDC_CLIP_FULL || (p.clip_mode == CDC_CLIP_HALF && b < p.B / 2);
+        if (p.variant == CDC_VARIANT_EPS || p.pred_mode == CDC_PRED_NOISE) {
+          x0v = cf.sqrt_recip_acp * xt - cf.sqrt_recipm1_acp * f;
+          if (clip) x0v = fminf(fmaxf(x0v, -1.f), 1.f);
+          noise = f;
+        } else {
+          x0v = (p.pred_mode == CDC_PRED_X) ? f : cf.sqrt_acp * xt - cf.sqrt_1m_acp * f;
+          if (clip) x0v = fminf(fmaxf(x0v, -1.f), 1.f);
+          noise = (cf.sqrt_recip_acp * xt - x0v) / cf.sqrt_recipm1_acp;
+        }
+        float xn = cf.sqrt_acp_prev * x0v + cf.dir_coef * noise;
+        if (p.z) xn += cf.noise_coef * p.z[idx];
+        p.x[idx] = xn;
+      }
+}
+
+}  // namespace cdc

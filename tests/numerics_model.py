@@ -1,0 +1,113 @@
+"""CPU emulation of the CUDA engine's *rounding points* (test infrastructure).
+
+The engine stores activations and weights as fp16 and accumulates in fp32.  This model
+re-runs the oracle's arithmetic in float64 but rounds to fp16 at exactly the places the
+kernels do, so the fp16 error budget (north_star: <= 1e-3 relative) can be checked on CPU
+before any kernel runs, and so a GPU mismatch can be split into "design rounding" vs "bug".
+Set ``ROUND = False`` to recover the oracle exactly (used as a self-test).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+ROUND = True
+
+
+def r16(x: torch.Tensor) -> torch.Tensor:
+    return x.half().to(x.dtype) if ROUND else x
+
+
+def _ln_stats(x, eps=1e-5):
+    var = x.var(dim=1, unbiased=False, keepdim=True)
+    mean = x.mean(dim=1, keepdim=True)
+    return mean, 1.0 / (var + eps).sqrt()
+
+
+def _block(sd, p, x16, post):
+    """x16 already fp16-rounded.  conv (fp16 w, wide accum) + bias -> LN -> ReLU -> post -> fp16."""
+    w = r16(sd[p + "block.0.weight"])
+    y = F.conv2d(x16, w, sd[p + "block.0.bias"], padding=w.shape[-1] // 2)
+    mean, rstd = _ln_stats(y)
+    y = (y - mean) * rstd * sd[p + "block.1.g"] + sd[p + "block.1.b"]
+    return r16(post(F.relu(y)))
+
+
+def _resnet(sd, p, x16, temb):
+    if temb is not None:
+        shift = F.linear(F.leaky_relu(temb, 0.2), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])[:, :, None, None]
+    else:
+        shift = 0.0
+    h = _block(sd, p + "block1.", x16, lambda v: v + shift)
+    if (p + "res_conv.weight") in sd:
+        r = r16(F.conv2d(x16, r16(sd[p + "res_conv.weight"]), sd[p + "res_conv.bias"]))
+    else:
+        r = x16
+    return _block(sd, p + "block2.", h, lambda v: v + r)
+
+
+def _attn(sd, p, x16):
+    b, c, h, w = x16.shape
+    n = h * w
+    g = sd[p + "fn.norm.g"].reshape(1, c)
+    bl = sd[p + "fn.norm.b"].reshape(c)
+    wqkv = sd[p + "fn.fn.to_qkv.weight"].reshape(3 * c, c)
+    wq, wkv = wqkv[:c], wqkv[c:]
+    wo = sd[p + "fn.fn.to_out.weight"].reshape(c, c)
+    bo = sd[p + "fn.fn.to_out.bias"]
+    mean, rstd = _ln_stats(x16)                      # stats of the stored (rounded) tensor
+    xf = x16.reshape(b, c, n)
+    mean, rstd = mean.reshape(b, 1, n), rstd.reshape(b, 1, n)
+    # K,V = rstd*(Wg x - mean*u) + c   (LayerNorm folded into the GEMM epilogue)
+    wg = r16(wkv * g)
+    u = wg.sum(dim=1)
+    cc = wkv @ bl
+    kv = rstd * (torch.einsum("oc,bcn->bon", wg, xf) - mean * u[None, :, None]) + cc[None, :, None]
+    k, v = kv[:, :c], kv[:, c:]
+    m = k.max(dim=-1, keepdim=True).values
+    pexp = r16(torch.exp(k - m))
+    s = torch.exp(k - m).sum(dim=-1)                 # fp32 sum of unrounded exps in the kernel
+    ctx = torch.einsum("bdn,ben->bde", pexp, r16(v)) / s[:, :, None]
+    # M_b = Wo ctx^T (scale Wq) ; out = rstd*(Mg x - mean*rowsum(Mg)) + M b_ln + bo + x
+    mb = torch.einsum("oe,bde,dc->boc", wo, ctx, wq * (c ** -0.5))
+    mg = r16(mb * g[None])
+    um = mg.sum(dim=2)
+    cm = torch.einsum("boc,c->bo", mb, bl) + bo[None]
+    out = rstd * (torch.einsum("boc,bcn->bon", mg, xf) - mean * um[:, :, None]) + cm[:, :, None] + xf
+    return r16(out.reshape(b, c, h, w))
+
+
+def unet_forward_emulated(sd, x, time, context: Sequence[torch.Tensor]):
+    from oracle import cdc_oracle as O
+    temb = O.time_embedding(sd, time) if time is not None else None
+    n_down = O._count(sd, "downs.")
+    n_up = O._count(sd, "ups.")
+    x = r16(x)
+    ctx16 = [r16(c) for c in context]
+    skips = []
+    for l in range(n_down):
+        p = f"downs.{l}."
+        if l < len(ctx16):
+            x = torch.cat([x, ctx16[l]], dim=1)
+        x = _resnet(sd, p + "0.", x, temb)
+        x = _resnet(sd, p + "1.", x, temb)
+        x = _attn(sd, p + "2.", x)
+        skips.append(x)
+        if (p + "3.conv.weight") in sd:
+            x = r16(F.conv2d(x, r16(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1))
+    x = _resnet(sd, "mid_block1.", x, temb)
+    x = _attn(sd, "mid_attn.", x)
+    x = _resnet(sd, "mid_block2.", x, temb)
+    for l in range(n_up):
+        p = f"ups.{l}."
+        x = torch.cat([x, skips.pop()], dim=1)
+        x = _resnet(sd, p + "0.", x, temb)
+        x = _resnet(sd, p + "1.", x, temb)
+        x = _attn(sd, p + "2.", x)
+        if (p + "3.conv.weight") in sd:
+            x = r16(F.conv_transpose2d(x, r16(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1))
+    mean, rstd = _ln_stats(x)
+    xn = r16((x - mean) * rstd * sd["final_conv.0.g"] + sd["final_conv.0.b"])
+    return F.conv2d(xn, r16(sd["final_conv.1.weight"]), sd["final_conv.1.bias"], padding=3)
