@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cdc_engine_num_ops": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "cdc_engine_op_name": (C.c_char_p, [_P, C.c_int]),
     "cdc_engine_set_debug": (C.c_int, [_P, C.c_int]),
+    "cdc_engine_profile_ops": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
     "cdc_engine_set_mainloop": (C.c_int, [_P, C.c_int]),
 }
 

@@ -157,15 +157,25 @@ struct Plan {
   // persistent region
   std::vector<size_t> ctx_off;     // fp16 NHWC context per level (level 0 of the eps variant: fp32 NCHW copy)
   size_t shifts_off = 0;
+  size_t xstate_off = 0;           // fp32 NCHW sampler state the captured graph works on
   int pack_op = -1, time_op = -1, final_op = -1;
   double flops = 0;
   // captured step graph
   cudaGraphExec_t graph = nullptr;
-  const float* graph_x = nullptr;
   int graph_pred = -1, graph_clip = -1;
 };
 
 }  // namespace
+
+struct RunArgs {
+  const float* x = nullptr;     // network input (fp32 NCHW)
+  const float* time = nullptr;  // [B] or null (use schedule table)
+  float* out = nullptr;         // mode 0
+  float* x_inout = nullptr;     // mode 1
+  const float* z = nullptr;
+  int mode = 0, pred = 0, clip = 0;
+  bool advance = false;
+};
 
 struct cdc_engine {
   cdc_config cfg{};
@@ -195,11 +205,16 @@ struct cdc_engine {
   cdc_step_coef* d_table = nullptr;
   int table_cap = 0, S = 0;
   int* d_step = nullptr;
+  // stream the sampling loop runs on (the caller's stream may be the legacy default stream, which
+  // cannot be captured); joined to the caller's stream with events on both sides
+  cudaStream_t loop_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // context state
   bool ctx_set = false;
   int ctx_B = 0, ctx_H = 0, ctx_W = 0;
   uintptr_t ctx_ws = 0;
   Plan* last_plan = nullptr;
+  RunArgs last_args;
 };
 
 namespace {
@@ -684,6 +699,7 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     else pl->ctx_off.push_back(take((size_t)B * c * h * w * 2));
   }
   pl->shifts_off = take((size_t)B * e->R * 4);
+  pl->xstate_off = take((size_t)B * cfg.channels * H * W * 4);
   bd.arena_base = off;
 
   // ---- ops ----
@@ -842,20 +858,10 @@ Plan* get_plan(cdc_engine* e, int B, int H, int W, void* ws, int* rc) {
   return raw;
 }
 
-struct RunArgs {
-  const float* x = nullptr;     // network input (fp32 NCHW)
-  const float* time = nullptr;  // [B] or null (use schedule table)
-  float* out = nullptr;         // mode 0
-  float* x_inout = nullptr;     // mode 1
-  const float* z = nullptr;
-  int mode = 0, pred = 0, clip = 0;
-  bool advance = false;
-};
-
-int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
+int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st) {
   const cdc_config& cfg = e->cfg;
   const int B = pl->B, H = pl->H, W = pl->W;
-  for (size_t i = 0; i < pl->ops.size(); ++i) {
+  {
     const Op& op = pl->ops[i];
     switch (op.kind) {
       case OP_TIME: {
@@ -924,10 +930,19 @@ int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
     if (err != cudaSuccess)
       return fail(e, CDC_ERR_CUDA, "launch of op %zu '%s' failed: %s", i, op.name.c_str(), cudaGetErrorString(err));
   }
+  return 0;
+}
+
+int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
+  for (size_t i = 0; i < pl->ops.size(); ++i) {
+    int rc = run_op(e, pl, i, a, st);
+    if (rc) return rc;
+  }
   if (a.advance) {
     advance_step_kernel<<<1, 32, 0, st>>>(e->d_step);
   }
   e->last_plan = pl;
+  e->last_args = a;
   return 0;
 }
 
@@ -1009,6 +1024,10 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) return fail(nullptr, CDC_ERR_UNSUPPORTED, "device sm_%d%d: this build targets sm_100a only", prop.major, prop.minor);
   if (cudaMalloc(&e->d_step, sizeof(int)) != cudaSuccess) return fail(nullptr, CDC_ERR_CUDA, "cudaMalloc failed");
+  if (cudaStreamCreateWithFlags(&e->loop_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess)
+    return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   *out = e.release();
@@ -1023,6 +1042,9 @@ void cdc_engine_destroy(cdc_engine* e) {
   if (e->dblob) cudaFree(e->dblob);
   if (e->d_table) cudaFree(e->d_table);
   if (e->d_step) cudaFree(e->d_step);
+  if (e->loop_stream) cudaStreamDestroy(e->loop_stream);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
   delete e;
 }
 
@@ -1263,12 +1285,19 @@ int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int 
   int rc = sampler_prologue(e, B, H, W, workspace, workspace_bytes, pred_mode, clip_mode, &pl);
   if (rc) return rc;
   if (i_first >= e->S || i_last < 0 || i_last > i_first) return fail(e, CDC_ERR_INVALID, "bad step range %d..%d (S=%d)", i_first, i_last, e->S);
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaStream_t st = e->loop_stream;
+  CUDA_TRY(e, cudaEventRecord(e->ev_in, caller));
+  CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_in, 0));
   int i_start = i_first;
-  if (!pl->graph || pl->graph_x != x_inout || pl->graph_pred != pred_mode || pl->graph_clip != clip_mode) {
+  // the loop state lives in the workspace so the captured graph does not depend on the caller's buffer
+  float* xs = reinterpret_cast<float*>(pl->ws + pl->xstate_off);
+  const size_t xbytes = (size_t)B * e->cfg.channels * H * W * 4;
+  CUDA_TRY(e, cudaMemcpyAsync(xs, x_inout, xbytes, cudaMemcpyDeviceToDevice, st));
+  if (!pl->graph || pl->graph_pred != pred_mode || pl->graph_clip != clip_mode) {
     if (pl->graph) { cudaGraphExecDestroy(pl->graph); pl->graph = nullptr; }
     RunArgs a;
-    a.x = x_inout; a.x_inout = x_inout; a.z = nullptr; a.mode = 1; a.pred = pred_mode; a.clip = clip_mode; a.advance = true;
+    a.x = xs; a.x_inout = xs; a.z = nullptr; a.mode = 1; a.pred = pred_mode; a.clip = clip_mode; a.advance = true;
     // The first step runs eagerly: it is real work AND it forces every kernel's module load /
     // attribute setup to happen before stream capture starts.
     set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
@@ -1283,11 +1312,14 @@ int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int 
     err = cudaGraphInstantiate(&pl->graph, g, 0);
     cudaGraphDestroy(g);
     if (err != cudaSuccess) { pl->graph = nullptr; return fail(e, CDC_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(err)); }
-    pl->graph_x = x_inout; pl->graph_pred = pred_mode; pl->graph_clip = clip_mode;
+    pl->graph_pred = pred_mode; pl->graph_clip = clip_mode;
   } else {
     set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
   }
   for (int i = i_start; i >= i_last; --i) CUDA_TRY(e, cudaGraphLaunch(pl->graph, st));
+  CUDA_TRY(e, cudaMemcpyAsync(x_inout, xs, xbytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(e, cudaEventRecord(e->ev_out, st));
+  CUDA_TRY(e, cudaStreamWaitEvent(caller, e->ev_out, 0));
   e->last_plan = pl;
   return CDC_OK;
 }
@@ -1334,6 +1366,37 @@ int64_t cdc_engine_debug_read(cdc_engine* e, int op_index, float* host_out, int6
   CUDA_TRY(e, cudaDeviceSynchronize());
   CUDA_TRY(e, cudaMemcpy(tmp.data(), op.dbg, (size_t)n * 2, cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n; ++i) host_out[i] = __half2float(tmp[(size_t)i]);
+  return n;
+}
+
+int cdc_engine_profile_ops(cdc_engine* e, int iters, float* ms_out, double* flops_out, int capacity, void* stream) {
+  if (!e || !e->last_plan) return fail(e, CDC_ERR_STATE, "no plan has run yet");
+  if (iters < 1 || !ms_out || !flops_out) return fail(e, CDC_ERR_INVALID, "bad profile arguments");
+  Plan* pl = e->last_plan;
+  const int n = (int)pl->ops.size();
+  if (capacity < n) return fail(e, CDC_ERR_INVALID, "profile buffers too small (%d ops)", n);
+  cudaSetDevice(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t a, b;
+  CUDA_TRY(e, cudaEventCreate(&a));
+  CUDA_TRY(e, cudaEventCreate(&b));
+  RunArgs args = e->last_args;
+  args.advance = false;
+  for (int i = 0; i < n; ++i) {
+    int rc = run_op(e, pl, (size_t)i, args, st);  // warm
+    if (rc) return rc;
+    CUDA_TRY(e, cudaEventRecord(a, st));
+    for (int k = 0; k < iters; ++k)
+      if ((rc = run_op(e, pl, (size_t)i, args, st))) return rc;
+    CUDA_TRY(e, cudaEventRecord(b, st));
+    CUDA_TRY(e, cudaEventSynchronize(b));
+    float ms = 0.f;
+    CUDA_TRY(e, cudaEventElapsedTime(&ms, a, b));
+    ms_out[i] = ms / iters;
+    flops_out[i] = pl->ops[i].flops;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
   return n;
 }
 

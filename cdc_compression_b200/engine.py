@@ -152,6 +152,14 @@ class DenoiserEngine:
                                                     C.byref(h), C.byref(w)), "debug_read")
         return out.reshape(-1, h.value, w.value, c.value)
 
+    def profile_ops(self, iters: int = 5):
+        """[(op name, avg ms, algorithmic FLOPs)] for the plan that ran last, each op timed alone."""
+        cap = 4096
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        n = self._check(self._lib.cdc_engine_profile_ops(self._h, iters, ms, fl, cap, self._stream()), "profile_ops")
+        return [(self._lib.cdc_engine_op_name(self._h, i).decode(), ms[i], fl[i]) for i in range(n)]
+
     # ------------------------------------------------------------------ compute
     def _ctx_array(self, context: Sequence[torch.Tensor], B, H, W):
         if len(context) != self.n_context:

@@ -132,6 +132,9 @@ int64_t cdc_engine_debug_read(cdc_engine* e, int op_index, float* host_out, int6
                               int* C, int* H, int* W);
 int cdc_engine_num_ops(cdc_engine* e, int B, int H, int W);
 const char* cdc_engine_op_name(cdc_engine* e, int op_index);
+/* Time every op of the last-run plan in isolation: `iters` back-to-back launches between two CUDA events on
+ * `stream`; writes average ms and the op's algorithmic FLOPs.  Returns the number of ops (synchronises). */
+int cdc_engine_profile_ops(cdc_engine* e, int iters, float* ms_out, double* flops_out, int capacity, void* stream);
 /* Debug: 1 = never reuse workspace buffers, so every op output survives until debug_read. */
 int cdc_engine_set_debug(cdc_engine* e, int no_reuse);
 /* Select the conv mainloop: 0 = mma.sync (HMMA) baseline kernels, 1 = tcgen05/TMA kernels. */

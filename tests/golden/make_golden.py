@@ -1,0 +1,82 @@
+"""Generate golden vectors by running the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+Imports the reference's modules from /root/reference (oracle/ref_loader.py), loads the
+deterministic weights of oracle.cdc_oracle.seeded_unet_state_dict, runs
+  * Unet.forward on seeded (x_t, time, context) at small sizes, both variants
+  * a short DDIM p_sample_loop (S steps) from a seeded init, both variants
+  * GaussianDiffusion.set_sample_schedule tables
+and writes tests/golden/*.npz (fp32).  The GPU box has no /root/reference: the tests there
+rebuild the same seeded inputs and compare against these files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import cdc_oracle as O  # noqa: E402
+from oracle.ref_loader import build_reference_diffusion  # noqa: E402
+
+CASES = [  # name, variant, B, H, W, seed, gain
+    ("eps_b2_64x96", "eps", 2, 64, 96, 0, 1.0),
+    ("x_b2_64x64", "x", 2, 64, 64, 0, 1.0),
+    ("eps_b1_32x32_smallgain", "eps", 1, 32, 32, 1, 0.5),
+    ("x_b1_96x64", "x", 1, 96, 64, 1, 1.0),
+]
+LOOPS = [  # name, variant, B, H, W, S, seed
+    ("eps_loop_s6", "eps", 2, 64, 64, 6, 0),
+    ("x_loop_s5", "x", 2, 64, 64, 5, 0),
+]
+
+
+def case_inputs(variant, B, H, W, seed):
+    ctx = O.seeded_context(variant, B, H, W, seed=seed)
+    g = torch.Generator().manual_seed(5 + seed)
+    x = torch.randn(B, 3, H, W, generator=g)
+    t = torch.linspace(0.15, 0.9, B)[:, None]
+    init = torch.randn(B, 3, H, W, generator=g) * 0.8
+    return x, t, ctx, init
+
+
+def main():
+    torch.set_grad_enabled(False)
+    for name, variant, B, H, W, seed, gain in CASES:
+        _, diff = build_reference_diffusion(variant, with_context_fn=False)
+        diff.denoise_fn.load_state_dict(O.seeded_unet_state_dict(variant, seed, gain=gain))
+        x, t, ctx, _ = case_inputs(variant, B, H, W, seed)
+        y = diff.denoise_fn(x, t, ctx)
+        np.savez_compressed(os.path.join(HERE, f"unet_{name}.npz"), out=y.numpy(),
+                            meta=np.array([B, H, W, seed], dtype=np.int64), gain=np.float32(gain))
+        print(name, tuple(y.shape), float(y.abs().mean()))
+    for name, variant, B, H, W, S, seed in LOOPS:
+        _, diff = build_reference_diffusion(variant, with_context_fn=False)
+        diff.denoise_fn.load_state_dict(O.seeded_unet_state_dict(variant, seed))
+        _, _, ctx, init = case_inputs(variant, B, H, W, seed)
+        diff.set_sample_schedule(S, torch.device("cpu"))
+        if variant == "eps":
+            out = diff.p_sample_loop(init.shape, ctx, "ddim", init=init.clone(), eta=0)
+        else:
+            out = diff.p_sample_loop(init.shape, ctx, clip_denoised=True, init=init.clone(), eta=0)
+        tables = {k: getattr(diff, k).numpy() for k in (
+            "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod_prev", "one_minus_alphas_cumprod_prev",
+            "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "sigma")}
+        np.savez_compressed(os.path.join(HERE, f"loop_{name}.npz"), out=out.numpy(),
+                            meta=np.array([B, H, W, S, seed], dtype=np.int64), **tables)
+        print(name, tuple(out.shape), float(out.abs().max()))
+    # schedule-only fixtures at the demo step counts
+    for variant, sched, T in (("eps", "linear", 20000), ("x", "cosine", 8193)):
+        _, diff = build_reference_diffusion(variant, with_context_fn=False)
+        for S in (1, 65, 500):
+            diff.set_sample_schedule(S, torch.device("cpu"))
+            np.savez_compressed(os.path.join(HERE, f"sched_{variant}_{S}.npz"),
+                                alphas_cumprod=diff.alphas_cumprod.numpy(), sigma=diff.sigma.numpy(),
+                                sqrt_recipm1_alphas_cumprod=diff.sqrt_recipm1_alphas_cumprod.numpy())
+
+
+if __name__ == "__main__":
+    main()

@@ -35,17 +35,26 @@ def _block(sd, p, x16, post):
     return r16(post(F.relu(y)))
 
 
+TAPS = None  # set to a dict to record per-op outputs under the engine's op names
+
+
+def _tap(name, t):
+    if TAPS is not None:
+        TAPS[name] = t
+    return t
+
+
 def _resnet(sd, p, x16, temb):
     if temb is not None:
         shift = F.linear(F.leaky_relu(temb, 0.2), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])[:, :, None, None]
     else:
         shift = 0.0
-    h = _block(sd, p + "block1.", x16, lambda v: v + shift)
+    h = _tap(p + "block1", _block(sd, p + "block1.", x16, lambda v: v + shift))
     if (p + "res_conv.weight") in sd:
-        r = r16(F.conv2d(x16, r16(sd[p + "res_conv.weight"]), sd[p + "res_conv.bias"]))
+        r = _tap(p + "res_conv", r16(F.conv2d(x16, r16(sd[p + "res_conv.weight"]), sd[p + "res_conv.bias"])))
     else:
         r = x16
-    return _block(sd, p + "block2.", h, lambda v: v + r)
+    return _tap(p + "block2", _block(sd, p + "block2.", h, lambda v: v + r))
 
 
 def _attn(sd, p, x16):
@@ -76,7 +85,7 @@ def _attn(sd, p, x16):
     um = mg.sum(dim=2)
     cm = torch.einsum("boc,c->bo", mb, bl) + bo[None]
     out = rstd * (torch.einsum("boc,bcn->bon", mg, xf) - mean * um[:, :, None]) + cm[:, :, None] + xf
-    return r16(out.reshape(b, c, h, w))
+    return _tap(p + "out", r16(out.reshape(b, c, h, w)))
 
 
 def unet_forward_emulated(sd, x, time, context: Sequence[torch.Tensor]):
@@ -96,7 +105,7 @@ def unet_forward_emulated(sd, x, time, context: Sequence[torch.Tensor]):
         x = _attn(sd, p + "2.", x)
         skips.append(x)
         if (p + "3.conv.weight") in sd:
-            x = r16(F.conv2d(x, r16(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1))
+            x = _tap(p + "3.down", r16(F.conv2d(x, r16(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1)))
     x = _resnet(sd, "mid_block1.", x, temb)
     x = _attn(sd, "mid_attn.", x)
     x = _resnet(sd, "mid_block2.", x, temb)
@@ -107,7 +116,8 @@ def unet_forward_emulated(sd, x, time, context: Sequence[torch.Tensor]):
         x = _resnet(sd, p + "1.", x, temb)
         x = _attn(sd, p + "2.", x)
         if (p + "3.conv.weight") in sd:
-            x = r16(F.conv_transpose2d(x, r16(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1))
+            x = _tap(p + "3.up", r16(F.conv_transpose2d(x, r16(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1)))
+    _tap("final_conv", x)
     mean, rstd = _ln_stats(x)
     xn = r16((x - mean) * rstd * sd["final_conv.0.g"] + sd["final_conv.0.b"])
     return F.conv2d(xn, r16(sd["final_conv.1.weight"]), sd["final_conv.1.bias"], padding=3)
