@@ -250,10 +250,16 @@ def run_ours(args):
 
     # ---- per-op timing (each op alone, CUDA events) -> dominant kernel + per-block table ----
     torch.cuda.synchronize()
-    eng.set_context(ctx, BATCH, HEIGHT, WIDTH)
+    model.set_sample_schedule(SCHEDULE, device)
     xs = init_d.clone().contiguous()
+    eng = model._bind(xs, ctx, 0.0)
+    eng.set_context(ctx, BATCH, HEIGHT, WIDTH)
     eng.ddim_step(xs, SCHEDULE - 1, None, "noise", "none")
     prof = eng.profile_ops(iters=5)
+    if args.ops_out:
+        with open(args.ops_out, "w") as f:
+            json.dump([{"op": n, "ms": m, "gflop": fl / 1e9, "tflops": (fl / (m * 1e-3) / 1e12) if m > 0 else 0.0}
+                       for n, m, fl in prof], f, indent=0)
     tot_ms = sum(p[1] for p in prof)
     fam = {}
     for name, pms, fl in prof:
@@ -305,6 +311,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops-out", default=None, help="write the per-op timing table (JSON) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -584,9 +584,10 @@ struct Builder {
                 const AttnW& w) {
     const int C = w.C, N = x.H * x.W, cb = C / 64;
     const int ntiles = (N + 63) / 64;
-    int nchunks = std::min(ntiles, std::max(1, 296 / (B * cb * cb)));
-    const int tpc = (ntiles + nchunks - 1) / nchunks;
-    nchunks = (ntiles + tpc - 1) / tpc;
+    // The split over pixels depends on (N, C) only — never on B — so every image goes through the same
+    // sequence of fp32 additions whatever batch it is decoded in (batch-invariant, bit-reproducible shards).
+    const int tpc = std::max(8, (ntiles + 63) / 64);
+    const int nchunks = (ntiles + tpc - 1) / tpc;
     const size_t pc_b = (size_t)B * nchunks * C * C * 4, pv_b = (size_t)B * nchunks * C * 4;
     const size_t pc = raw_alloc(pc_b), pm = raw_alloc(pv_b), ps = raw_alloc(pv_b);
     {
@@ -866,7 +867,7 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
     switch (op.kind) {
       case OP_TIME: {
         const size_t sm = (size_t)5 * cfg.dim * 4;
-        time_mlp_kernel<<<B, 256, sm, st>>>(a.time, a.time ? nullptr : e->d_table, e->d_step,
+        time_mlp_kernel<<<dim3(B, (e->R + 255) / 256), 256, sm, st>>>(a.time, a.time ? nullptr : e->d_table, e->d_step,
                                             dptr<float>(e, e->t_w1), dptr<float>(e, e->t_b1), dptr<float>(e, e->t_w2),
                                             dptr<float>(e, e->t_b2), dptr<float>(e, e->t_wcat),
                                             dptr<float>(e, e->t_bcat), cfg.dim, e->R,

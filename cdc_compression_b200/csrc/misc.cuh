@@ -76,14 +76,19 @@ __global__ void time_mlp_kernel(const float* __restrict__ time, const cdc_step_c
     hid[j] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < dim; j += blockDim.x) {
-    float a = b2[j];
+  for (int j = threadIdx.x >> 2; j < dim; j += blockDim.x >> 2) {   // 4 lanes per output
     const float* w = W2 + (size_t)j * 4 * dim;
-    for (int k = 0; k < 4 * dim; ++k) a = fmaf(w[k], hid[k], a);
-    act[j] = a > 0.f ? a : 0.2f * a;
+    float a = 0.f;
+    for (int k = threadIdx.x & 3; k < 4 * dim; k += 4) a = fmaf(w[k], hid[k], a);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += b2[j];
+    if ((threadIdx.x & 3) == 0) act[j] = a > 0.f ? a : 0.2f * a;
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+  // blockIdx.y selects a 256-row slice of the concatenated per-block Linear layers (temb is recomputed per CTA)
+  const int r = blockIdx.y * blockDim.x + threadIdx.x;
+  if (r < R) {
     float a = bcat[r];
     const float* w = Wcat + (size_t)r * dim;
     for (int k = 0; k < dim; ++k) a = fmaf(w[k], act[k], a);

@@ -81,7 +81,7 @@ def test_batch_elements_are_independent(variant):
     yb = d.denoise_fn(x.to(dev()), t.to(dev()), [c.to(dev()) for c in ctx])
     for i in range(B):
         yi = d.denoise_fn(x[i:i + 1].to(dev()), t[i:i + 1].to(dev()), [c[i:i + 1].to(dev()) for c in ctx])
-        assert rel(yb[i:i + 1], yi) < 5e-4      # split-N attention partials reorder fp32 sums; nothing else differs
+        assert torch.equal(yb[i:i + 1], yi)     # batch-invariant: no kernel's summation order depends on B
 
 
 def _coefs(sch, variant, eta=0.0):
@@ -191,7 +191,7 @@ def test_compress_dropin_end_to_end(variant):
     assert out.shape == img.shape and torch.isfinite(out).all() and torch.isfinite(bpp).all()
     T, sched = (20000, "linear") if variant == "eps" else (8193, "cosine")
     sch = O.make_sample_schedule(O.train_alphas_cumprod(sched, T), S, variant)
-    ref = O.sample_loop(O.sub_state_dict(d.state_dict(), "denoise_fn."), sch, variant,
+    ref = O.sample_loop(O.sub_state_dict({k: v.cpu() for k, v in d.state_dict().items()}, "denoise_fn."), sch, variant,
                         [c.cpu() for c in ctx], init.clone())
     to01 = lambda v: v.cpu().clamp(-1, 1) / 2 + 0.5
     psnr = O.batch_psnr(to01(out), to01(ref))
@@ -242,4 +242,4 @@ def test_large_shape_512_runs_and_is_finite():
     y2 = d.denoise_fn(x.to(dev()), t.to(dev()), [c.to(dev()) for c in ctx])
     y1 = d.denoise_fn(x[:1].to(dev()), t[:1].to(dev()), [c[:1].to(dev()) for c in ctx])
     assert torch.isfinite(y2).all()
-    assert rel(y2[:1], y1) < 5e-4
+    assert torch.equal(y2[:1], y1)
