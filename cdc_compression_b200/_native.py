@@ -56,6 +56,7 @@ _SIGNATURES = {
     "cdc_engine_set_debug": (C.c_int, [_P, C.c_int]),
     "cdc_engine_profile_ops": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
     "cdc_engine_set_mainloop": (C.c_int, [_P, C.c_int]),
+    "cdc_engine_tc_ops": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
 }
 
 

@@ -21,6 +21,7 @@
 #include "../../include/cdc_b200.h"
 #include "attn.cuh"
 #include "igemm_hmma.cuh"
+#include "igemm_tc.cuh"
 #include "misc.cuh"
 
 using namespace cdc;
@@ -94,6 +95,11 @@ struct Op {
   struct { const float *pc, *pm, *ps; int C, nchunks; float* out; } comb{};
   struct { const float *At, *Bm; float* Cout; int M, N, K; long long sA, sB, sC; } sg{};
   struct { const float *Mf, *g, *bln, *bout; int C; __half* Mg; float *um, *cm; } fin{};
+  // tcgen05 path (stride-1 convolutions when the engine's mainloop is 1)
+  bool use_tc = false;
+  CUtensorMap maps[4];
+  TcConvParams tcp{};
+  int tc_grid = 0, tc_smem = 0;
   // debug view of the op's fp16 NHWC output (if any)
   const __half* dbg = nullptr;
   int dC = 0, dH = 0, dW = 0;
@@ -185,7 +191,8 @@ struct cdc_engine {
   bool finalized = false;
   bool dry = false;  // created with device == -1: planning only
   bool debug_no_reuse = false;
-  int mainloop = 0;
+  int mainloop = 1;   // 0 = mma.sync kernels, 1 = tcgen05/TMA kernels for stride-1 convolutions (default)
+  int num_sms = 148;
   // derived structure
   std::vector<int> dims, cdims;
   bool fold_ctx0 = false;  // small level-0 context folded into the packed input (eps demo)
@@ -682,6 +689,104 @@ struct Builder {
   }
 };
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int pow2floor(int v) {
+  int r = 1;
+  while (r * 2 <= v) r *= 2;
+  return r;
+}
+
+// Route a stride-1 convolution op to the tcgen05/TMA kernel: tile geometry, pipeline depth, tensor maps.
+int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
+  const ConvParams& c = op.conv;
+  op.use_tc = false;
+  if (e->mainloop != 1 || c.stride != 1) return 0;
+  const int B = pl->B, h = c.Hs, w = c.Ws, N = c.Ntot;
+  TcConvParams t{};
+  t.TW = std::min(16, pow2floor(w));
+  if (c.groups > 1) {  // per-image weights: a tile must stay inside one image
+    t.TB = 1;
+    t.TH = 128 / t.TW;
+    if (pow2floor(h) < t.TH) return 0;
+  } else {
+    t.TH = std::min(128 / t.TW, pow2floor(h));
+    t.TB = 128 / (t.TW * t.TH);
+    if (t.TB > B) return 0;
+  }
+  t.tiles_x = (w + t.TW - 1) / t.TW;
+  t.tiles_y = (h + t.TH - 1) / t.TH;
+  t.tiles_b = (B + t.TB - 1) / t.TB;
+  t.B = B; t.H = h; t.W = w;
+  t.nseg = c.nseg;
+  for (int i = 0; i < c.nseg; ++i) {
+    t.seg[i].cpt = c.seg[i].C / 64;
+    t.seg[i].kh = c.seg[i].kh; t.seg[i].kw = c.seg[i].kw;
+    t.seg[i].dy0 = c.seg[i].dy0; t.seg[i].dx0 = c.seg[i].dx0;
+    t.seg[i].nchunk = c.seg[i].nchunk;
+  }
+  t.total_chunks = c.total_chunks;
+  t.Ntot = N;
+  t.n_split = N > 256 ? 2 : 1;
+  t.n_piece = N / t.n_split;
+  t.nbuf = (2 * N <= 512) ? 2 : 1;
+  const int budget = 227 * 1024 - 1024 - 5 * 384 * 4 - 256;
+  t.stages = std::max(2, std::min(kTcMaxStages, budget / tc_stage_bytes(N)));
+  t.phases = c.phases ? 4 : 1;
+  t.w_rows_per_phase = c.total_chunks * N;
+  t.w_rows_per_image = c.groups > 1 ? c.total_chunks * N : 0;
+  t.epi = op.epi;
+  t.out = c.out; t.out_H = c.out_H; t.out_W = c.out_W; t.out_sy = c.out_sy; t.out_sx = c.out_sx;
+  t.bias = c.bias; t.ln_g = c.ln_g; t.ln_b = c.ln_b; t.shift = c.shift; t.shift_stride = c.shift_stride;
+  t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2;
+  t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
+  op.tcp = t;
+  op.tc_smem = tc_smem_bytes(N, t.stages);
+  op.tc_grid = std::min(t.tiles_x * t.tiles_y * t.tiles_b * t.phases, e->num_sms);
+  op.use_tc = true;
+  if (!pl->ws) return 0;  // dry run: geometry only
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  for (int i = 0; i < c.nseg; ++i) {
+    const cuuint64_t Cs = (cuuint64_t)c.seg[i].C;
+    cuuint64_t gdim[4] = {Cs, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {Cs * 2, (cuuint64_t)w * Cs * 2, (cuuint64_t)h * w * Cs * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)t.TW, (cuuint32_t)t.TH, (cuuint32_t)t.TB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&op.maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)c.seg[i].src, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(A, op %s, seg %d) failed: %d", op.name.c_str(), i, (int)r);
+  }
+  for (int i = c.nseg; i < 3; ++i) op.maps[i] = op.maps[0];
+  {
+    const cuuint64_t rows = (cuuint64_t)(c.groups > 1 ? B : t.phases) * c.total_chunks * N;
+    cuuint64_t gdim[2] = {64, rows};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)t.n_piece};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&op.maps[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)c.W, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(B, op %s) failed: %d", op.name.c_str(), (int)r);
+  }
+  return 0;
+}
+
 int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
   const cdc_config& cfg = e->cfg;
   const int L = cfg.n_levels;
@@ -829,6 +934,11 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
   }
   bd.drop(x);
   pl->total_bytes = bd.arena_base + bd.arena.peak;
+  for (auto& op : pl->ops)
+    if (op.kind == OP_CONV) {
+      int rc = setup_tc(e, pl, op);
+      if (rc) return rc;
+    }
   pl->flops = 0;
   for (auto& op : pl->ops) pl->flops += op.flops;
   return 0;
@@ -883,6 +993,11 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         break;
       }
       case OP_CONV: {
+        if (op.use_tc) {
+          igemm_tc_kernel<<<op.tc_grid, kTcThreads, op.tc_smem, st>>>(op.maps[0], op.maps[1], op.maps[2], op.maps[3],
+                                                                      op.tcp);
+          break;
+        }
         cudaError_t err = launch_igemm(op, st);
         if (err != cudaSuccess)
           return fail(e, CDC_ERR_CUDA, "conv launch '%s' (bm=%d bn=%d epi=%d): %s", op.name.c_str(), op.bm, op.bn,
@@ -1029,6 +1144,8 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
       cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess)
     return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
+  e->num_sms = prop.multiProcessorCount;
+  cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   *out = e.release();
@@ -1413,9 +1530,23 @@ int cdc_engine_set_debug(cdc_engine* e, int no_reuse) {
 
 int cdc_engine_set_mainloop(cdc_engine* e, int kind) {
   if (!e) return CDC_ERR_INVALID;
-  if (kind != 0) return fail(e, CDC_ERR_UNSUPPORTED, "mainloop %d not built", kind);
+  if (kind != 0 && kind != 1) return fail(e, CDC_ERR_UNSUPPORTED, "mainloop %d not built", kind);
   e->mainloop = kind;
+  for (auto& kv : e->plans) if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+  e->plans.clear();
+  e->last_plan = nullptr;
+  e->ctx_set = false;
   return CDC_OK;
+}
+
+int cdc_engine_tc_ops(cdc_engine* e, int B, int H, int W) {
+  if (!e || !e->finalized) return fail(e, CDC_ERR_STATE, "engine not finalized");
+  Plan pl;
+  int rc = build_plan(e, &pl, B, H, W, nullptr);
+  if (rc) return rc;
+  int n = 0;
+  for (auto& op : pl.ops) n += op.use_tc ? 1 : 0;
+  return n;
 }
 
 }  // extern "C"

@@ -1,0 +1,448 @@
+// Implicit-GEMM convolution on the Blackwell tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM.
+//
+// Same GEMM view and fused epilogues as igemm_hmma.cuh (reference: Block / ResnetBlock / Upsample /
+// res_conv / attention output, epsilonparam/modules/network_components.py:34-42, 83-114, 117-139),
+// for stride-1 convolutions:
+//   * an output tile is 128 pixels = TB x TH x TW (images x rows x cols); one 4-D TMA box
+//     {64 channels, TW, TH, TB} per (tap, 64-channel chunk) lands as a K-major SWIZZLE_128B operand
+//     [128 rows][64 x fp16]; conv padding and ragged tile edges are TMA out-of-bounds zero fill.
+//   * the weight tile [C_out rows][64 x fp16] of the same K chunk is a 2-D TMA box from the repacked
+//     weights [chunk][C_out][64].
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=C_out split into pieces of
+//     <= 256) accumulating fp32 in TMEM; tcgen05.commit releases smem stages / publishes the accumulator.
+//   * 4 epilogue warps own one pixel row each (TMEM lane == GEMM row): bias, channel LayerNorm (exact
+//     two-pass variance from the fp32 accumulator), ReLU, timestep shift or residual, fp16 NHWC store.
+//   * persistent CTAs walk tiles with a static stride; the accumulator is double-buffered in TMEM when
+//     2*C_out <= 512 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue (TMEM lane quadrant = warp%4).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "igemm_hmma.cuh"  // EpiKind
+
+namespace cdc {
+
+struct TcSeg {
+  int cpt;       // 64-channel chunks per tap
+  int kh, kw;
+  int dy0, dx0;
+  int nchunk;
+};
+
+struct TcConvParams {
+  int TW, TH, TB;            // tile = TB x TH x TW = 128 pixels
+  int tiles_x, tiles_y, tiles_b;
+  int B, H, W;               // tile-space (== source) extents
+  int nseg;
+  TcSeg seg[kMaxSeg];
+  int total_chunks;
+  int Ntot;                  // C_out
+  int n_split, n_piece;      // UMMA N pieces (n_piece <= 256, n_piece % 16 == 0)
+  int nbuf;                  // TMEM accumulator buffers (1 or 2)
+  int stages;                // smem pipeline depth
+  int phases;                // 1, or 4 for the transposed-conv output phases
+  int w_rows_per_phase;      // weight rows between phases ( = total_chunks * Ntot )
+  int w_rows_per_image;      // per-image weights (attention): rows between images, else 0
+  int epi;
+  __half* out;               // NHWC fp16 [B, out_H, out_W, Ntot]
+  int out_H, out_W, out_sy, out_sx;
+  const float* bias;
+  const float* ln_g;
+  const float* ln_b;
+  const float* shift;
+  int shift_stride;
+  const __half* res;
+  int res_C0;
+  const __half* res2;
+  const float2* stats_in;
+  const float* aff_u;        // [B][Ntot] (per image)
+  const float* aff_c;
+  float2* stats_out;
+};
+
+__device__ __forceinline__ const __half* res_ptr_tc(const TcConvParams& p, long long pix, int col) {
+  if (col < p.res_C0) return p.res + (size_t)pix * p.res_C0 + col;
+  return p.res2 + (size_t)pix * (p.Ntot - p.res_C0) + (col - p.res_C0);
+}
+
+namespace tc {
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug traps (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 6000000000LL) {  // ~3 s at 1.9 GHz
+      printf("cdc igemm_tc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major SWIZZLE_128B operand descriptor: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 accumulate, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+}  // namespace tc
+
+constexpr int kTcThreads = 192;
+constexpr int kTcMaxStages = 8;
+
+// dynamic smem: [stages][A 16 KB | B Ntot*128 B] (1024-aligned) + epilogue vectors + barriers
+__host__ __device__ inline int tc_stage_bytes(int Ntot) { return 16384 + Ntot * 128; }
+__host__ __device__ inline int tc_smem_bytes(int Ntot, int stages) {
+  return 1024 /*alignment slack*/ + stages * tc_stage_bytes(Ntot) + 5 * 384 * 4 + 256;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+                const TcConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int stage_bytes = tc_stage_bytes(p.Ntot);
+  float* s_vec = reinterpret_cast<float*>(smem + p.stages * stage_bytes);  // bias | g | b | (u | c): 5 x 384
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + 5 * 384 * 4);
+  // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2]; then the TMEM base address word
+  const uint32_t bar_full = smem_u32(s_bar);
+  const uint32_t bar_empty = bar_full + 8 * kTcMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kTcMaxStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kTcMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.Ntot;
+  int tmem_cols = 32;
+  while (tmem_cols < p.nbuf * N) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&mapA0);
+    if (p.nseg > 1) tc::prefetch_tmap(&mapA1);
+    if (p.nseg > 2) tc::prefetch_tmap(&mapA2);
+    tc::prefetch_tmap(&mapB);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(bar_full + 8 * s, 1);
+      tc::mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < p.nbuf; ++b) {
+      tc::mbar_init(bar_tfull + 8 * b, 1);
+      tc::mbar_init(bar_tempty + 8 * b, 128);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  // epilogue vectors -> smem (all threads)
+  for (int i = threadIdx.x; i < N; i += kTcThreads) {
+    s_vec[i] = p.bias ? p.bias[i] : 0.f;
+    s_vec[384 + i] = p.ln_g ? p.ln_g[i] : 1.f;
+    s_vec[768 + i] = p.ln_b ? p.ln_b[i] : 0.f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int tiles_per_phase = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int total_tiles = tiles_per_phase * p.phases;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ph = t / tiles_per_phase;
+        int r = t - ph * tiles_per_phase;
+        const int tb = r / (p.tiles_x * p.tiles_y);
+        r -= tb * p.tiles_x * p.tiles_y;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB;
+        const int dyp = p.phases > 1 ? (ph >> 1) - 1 : 0, dxp = p.phases > 1 ? (ph & 1) - 1 : 0;
+        const int wrow0 = ph * p.w_rows_per_phase + b0 * p.w_rows_per_image;
+        int q = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const TcSeg sg = p.seg[s];
+          const CUtensorMap* mA = s == 0 ? &mapA0 : (s == 1 ? &mapA1 : &mapA2);
+          for (int ky = 0; ky < sg.kh; ++ky)
+            for (int kx = 0; kx < sg.kw; ++kx)
+              for (int cc = 0; cc < sg.cpt; ++cc, ++q) {
+                tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t sA = base + stage * stage_bytes;
+                const uint32_t sB = sA + 16384;
+                const uint32_t full = bar_full + 8 * stage;
+                tc::mbar_expect_tx(full, (uint32_t)stage_bytes);
+                tc::tma_load_4d(sA, mA, full, cc * 64, x0 + kx + sg.dx0 + dxp, y0 + ky + sg.dy0 + dyp, b0);
+                for (int pc = 0; pc < p.n_split; ++pc)
+                  tc::tma_load_2d(sB + pc * p.n_piece * 128, &mapB, full, 0, wrow0 + q * N + pc * p.n_piece);
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_f16(p.n_piece);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int buf = it % p.nbuf;
+        const uint32_t use = (uint32_t)(it / p.nbuf);  // how many times this buffer was used before
+        tc::mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+        for (int q = 0; q < p.total_chunks; ++q) {
+          tc::mbar_wait(bar_full + 8 * stage, phase);
+          tc::tc_fence_after();
+          const uint32_t sA = base + stage * stage_bytes;
+          const uint32_t sB = sA + 16384;
+          const uint64_t dA = tc::make_desc_sw128(sA);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            for (int pc = 0; pc < p.n_split; ++pc) {
+              const uint64_t dB = tc::make_desc_sw128(sB + pc * p.n_piece * 128);
+              tc::umma_f16(d_tmem + pc * p.n_piece, dA + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), idesc,
+                           (q | ks) ? 1u : 0u);
+            }
+          }
+          tc::umma_commit(bar_empty + 8 * stage);  // frees this smem stage once the MMAs above retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc::umma_commit(bar_tfull + 8 * buf);  // accumulator of this tile complete
+      }
+    }
+  } else {
+    // =============================== epilogue (4 warps, one GEMM row per thread) ===============================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // GEMM row == TMEM lane
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int buf = it % p.nbuf;
+      const uint32_t use = (uint32_t)(it / p.nbuf);
+      const int ph = t / tiles_per_phase;
+      int r = t - ph * tiles_per_phase;
+      const int tb = r / (p.tiles_x * p.tiles_y);
+      r -= tb * p.tiles_x * p.tiles_y;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int lx = row % p.TW, ly = (row / p.TW) % p.TH, lb = row / (p.TW * p.TH);
+      const int xx = tx * p.TW + lx, yy = ty * p.TH + ly, bb = tb * p.TB + lb;
+      const bool valid = xx < p.W && yy < p.H && bb < p.B;
+      const int py = p.phases > 1 ? (ph >> 1) : 0, px = p.phases > 1 ? (ph & 1) : 0;
+      const long long opix = ((long long)bb * p.out_H + yy * p.out_sy + py) * p.out_W + xx * p.out_sx + px;
+      __half* orow = p.out + (size_t)(valid ? opix : 0) * N;
+
+      tc::mbar_wait(bar_tfull + 8 * buf, use & 1);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * N);
+      uint32_t v[32];
+
+      if (p.epi == EPI_BIAS || p.epi == EPI_AFFINE) {
+        float mean = 0.f, rstd = 1.f;
+        const float* au = nullptr;
+        const float* ac = nullptr;
+        if (p.epi == EPI_AFFINE) {
+          if (valid) {
+            const float2 st = p.stats_in[opix];
+            mean = st.x;
+            rstd = st.y;
+          }
+          au = p.aff_u + (size_t)(valid ? bb : 0) * N;
+          ac = p.aff_c + (size_t)(valid ? bb : 0) * N;
+        }
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          tc::tmem_ld32(taddr + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float a = __uint_as_float(v[j + k]);
+                o[k] = p.epi == EPI_AFFINE ? rstd * (a - mean * au[c0 + j + k]) + ac[c0 + j + k] : a + s_vec[c0 + j + k];
+              }
+              if (p.res) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(res_ptr_tc(p, opix, c0 + j));
+                float2 f;
+                f = unpack_half2(rr.x); o[0] += f.x; o[1] += f.y;
+                f = unpack_half2(rr.y); o[2] += f.x; o[3] += f.y;
+                f = unpack_half2(rr.z); o[4] += f.x; o[5] += f.y;
+                f = unpack_half2(rr.w); o[6] += f.x; o[7] += f.y;
+              }
+              uint4 w;
+              w.x = pack_half2(o[0], o[1]);
+              w.y = pack_half2(o[2], o[3]);
+              w.z = pack_half2(o[4], o[5]);
+              w.w = pack_half2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(orow + c0 + j) = w;
+            }
+          }
+        }
+      } else {
+        // ---- channel LayerNorm: exact two-pass statistics from the fp32 accumulator ----
+        float sum = 0.f;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          tc::tmem_ld32(taddr + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]) + s_vec[c0 + j];
+        }
+        const float mean = sum / (float)N;
+        float sq = 0.f;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          tc::tmem_ld32(taddr + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(v[j]) + s_vec[c0 + j] - mean;
+            sq += d * d;
+          }
+        }
+        const float rstd = 1.f / sqrtf(sq / (float)N + 1e-5f);
+        const float* shift = (p.epi == EPI_LN_SHIFT && p.shift) ? p.shift + (size_t)(valid ? bb : 0) * p.shift_stride : nullptr;
+        float osum = 0.f, osq = 0.f;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          tc::tmem_ld32(taddr + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int c = c0 + j + k;
+                const float y = (__uint_as_float(v[j + k]) + s_vec[c] - mean) * rstd * s_vec[384 + c] + s_vec[768 + c];
+                o[k] = fmaxf(y, 0.f);
+                if (shift) o[k] += shift[c];
+              }
+              if (p.epi == EPI_LN_RES && p.res) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(res_ptr_tc(p, opix, c0 + j));
+                float2 f;
+                f = unpack_half2(rr.x); o[0] += f.x; o[1] += f.y;
+                f = unpack_half2(rr.y); o[2] += f.x; o[3] += f.y;
+                f = unpack_half2(rr.z); o[4] += f.x; o[5] += f.y;
+                f = unpack_half2(rr.w); o[6] += f.x; o[7] += f.y;
+              }
+              uint4 w;
+              w.x = pack_half2(o[0], o[1]);
+              w.y = pack_half2(o[2], o[3]);
+              w.z = pack_half2(o[4], o[5]);
+              w.w = pack_half2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(orow + c0 + j) = w;
+              if (p.stats_out) {  // statistics of the rounded values the consumer will read
+                float2 f;
+                f = unpack_half2(w.x); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+                f = unpack_half2(w.y); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+                f = unpack_half2(w.z); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+                f = unpack_half2(w.w); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+              }
+            }
+          }
+        }
+        if (p.stats_out && valid) {
+          const float m = osum / (float)N;
+          const float var = fmaxf(osq / (float)N - m * m, 0.f);
+          p.stats_out[opix] = make_float2(m, 1.f / sqrtf(var + 1e-5f));
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+}  // namespace cdc

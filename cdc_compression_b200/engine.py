@@ -132,6 +132,14 @@ class DenoiserEngine:
             raise EngineError("flops_per_forward failed: " + self._lib.cdc_last_error(self._h).decode())
         return v
 
+    def set_mainloop(self, kind: int):
+        """0 = mma.sync (HMMA) kernels, 1 = tcgen05/TMA kernels for the stride-1 convolutions."""
+        self._check(self._lib.cdc_engine_set_mainloop(self._h, int(kind)), "cdc_engine_set_mainloop")
+        self._ws_shape = None
+
+    def tc_ops(self, B, H, W) -> int:
+        return self._check(self._lib.cdc_engine_tc_ops(self._h, B, H, W), "cdc_engine_tc_ops")
+
     def set_debug(self, no_reuse: bool):
         self._check(self._lib.cdc_engine_set_debug(self._h, int(no_reuse)), "cdc_engine_set_debug")
         self._ws_shape = None

@@ -139,6 +139,8 @@ int cdc_engine_profile_ops(cdc_engine* e, int iters, float* ms_out, double* flop
 int cdc_engine_set_debug(cdc_engine* e, int no_reuse);
 /* Select the conv mainloop: 0 = mma.sync (HMMA) baseline kernels, 1 = tcgen05/TMA kernels. */
 int cdc_engine_set_mainloop(cdc_engine* e, int kind);
+/* How many ops of the plan for this shape run on the tcgen05/TMA kernel under the current mainloop. */
+int cdc_engine_tc_ops(cdc_engine* e, int B, int H, int W);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-taps", action="store_true")
     ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--mainloop", type=int, default=0)
     args = ap.parse_args()
     lines = []
 
@@ -52,7 +53,9 @@ def main():
     sd = O.seeded_unet_state_dict(variant, args.seed)
     eng = DenoiserEngine(variant, 64, (1, 2, 3, 4, 5, 6), (1, 2, 3, 4), 3, cc, dev)
     eng.load_weights(sd)
+    eng.set_mainloop(args.mainloop)
     eng.set_debug(not args.no_taps)
+    say(f"mainloop={args.mainloop} tc_ops={eng.tc_ops(B, H, W)}")
     ctx = O.seeded_context(variant, B, H, W, seed=args.seed)
     g = torch.Generator().manual_seed(5 + args.seed)
     x = torch.randn(B, 3, H, W, generator=g)

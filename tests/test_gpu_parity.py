@@ -73,6 +73,33 @@ def test_unet_forward_vs_oracle_and_emulator(variant):
 
 
 @pytest.mark.parametrize("variant", ["eps", "x"])
+def test_tcgen05_and_hmma_mainloops_agree(variant):
+    """The tcgen05/TMA convolution kernel (default) and the mma.sync baseline kernel implement the same rounding
+    points: the first Block's output may differ only by fp32 summation order, and both meet the tolerance."""
+    B, H, W, seed = 2, 64, 96, 0       # 96-wide: ragged 16-pixel tiles at every level
+    d = unet_on_gpu(variant, seed)
+    eng = d.denoise_fn.engine_for(dev())
+    x, t, ctx, _ = case_inputs(variant, B, H, W, seed)
+    ctxd = [c.to(dev()) for c in ctx]
+    outs, first = {}, {}
+    try:
+        for kind in (0, 1):
+            eng.set_mainloop(kind)
+            eng.set_debug(True)
+            assert (eng.tc_ops(B, H, W) > 0) == (kind == 1)
+            outs[kind] = eng.forward(x.to(dev()), t.reshape(-1).to(dev()), ctxd).cpu()
+            names = eng.debug_ops(B, H, W)
+            first[kind] = eng.debug_read(names.index("downs.0.0.block1"))
+    finally:
+        eng.set_debug(False)
+        eng.set_mainloop(1)
+    assert rel(first[1], first[0]) < 5e-5
+    sd64 = {k: v.double() for k, v in O.seeded_unet_state_dict(variant, seed).items()}
+    y64 = O.unet_forward(sd64, x.double(), t.double(), [c.double() for c in ctx])
+    assert rel(outs[0], y64) < REL_L2_UNET and rel(outs[1], y64) < REL_L2_UNET
+
+
+@pytest.mark.parametrize("variant", ["eps", "x"])
 def test_batch_elements_are_independent(variant):
     B, H, W, seed = 3, 32, 64, 0
     d = unet_on_gpu(variant, seed)
