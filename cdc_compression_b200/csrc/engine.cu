@@ -97,7 +97,7 @@ struct Op {
   struct { const float *Mf, *g, *bln, *bout; int C; __half* Mg; float *um, *cm; } fin{};
   // tcgen05 path (stride-1 convolutions when the engine's mainloop is 1)
   bool use_tc = false;
-  CUtensorMap maps[4];
+  TcMaps maps;
   TcConvParams tcp{};
   int tc_grid = 0, tc_smem = 0;
   // debug view of the op's fp16 NHWC output (if any)
@@ -150,8 +150,9 @@ struct Arena {
   }
 };
 
-struct Act {  // fp16 NHWC activation in the workspace
+struct Act {  // fp16 NHWC activation in the workspace (+ optional compensation tensor of the same shape)
   size_t off = 0, bytes = 0;
+  size_t off_lo = 0;  // 0 = none.  value = hi + lo, lo = fp16(value - hi): kept for the "trunk" activations
   int C = 0, H = 0, W = 0;
 };
 
@@ -280,7 +281,21 @@ struct SegSpec {  // how one K-segment of a conv maps onto the reference's OIHW 
                   // 2: packed input X0, 1x1 conv: k = 3*8 + c <- W[o][coff + c][0][0]
   int coff;       // first reference input channel of this segment
   int creal;      // real channels (mode 1/2)
+  int part = 0;   // 0: fp16(w)   1: fp16(w - fp16(w))  (weight compensation term of the 3-pass trunk convolutions)
 };
+
+// the three passes  x_hi*W_hi + x_lo*W_hi + x_hi*W_lo  of a precision-critical ("trunk") convolution
+std::vector<SegSpec> three_pass(const std::vector<SegSpec>& base, const std::vector<bool>& has_lo) {
+  std::vector<SegSpec> out = base;
+  for (size_t i = 0; i < base.size(); ++i)
+    if (has_lo[i]) out.push_back(base[i]);
+  for (size_t i = 0; i < base.size(); ++i) {
+    SegSpec s = base[i];
+    s.part = 1;
+    out.push_back(s);
+  }
+  return out;
+}
 
 // OIHW conv weight -> [chunk][N][64] fp16
 int pack_conv(cdc_engine* e, const std::string& key, int N, int Cin_ref, int KH, int KW,
@@ -313,7 +328,9 @@ int pack_conv(cdc_engine* e, const std::string& key, int N, int Cin_ref, int KH,
                 const int kx = k >> 3, c = k & 7;
                 if (kx == 3 && c < s.creal) v = w->data[((size_t)o * Cin_ref + s.coff + c)];
               }
-              tmp[((size_t)q * N + o) * 64 + k] = __float2half_rn(v);
+              __half hv = __float2half_rn(v);
+              if (s.part == 1) hv = __float2half_rn(v - __half2float(hv));
+              tmp[((size_t)q * N + o) * 64 + k] = hv;
             }
   }
   memcpy(e->blob.at<__half>(out->w), tmp.data(), tmp.size() * 2);
@@ -333,24 +350,27 @@ int pack_convT(cdc_engine* e, const std::string& key, int Cin, int Cout, ConvW* 
   const HostTensor* b = find(e, key + ".bias", {Cout}, &rc);
   if (!b) return rc;
   const int cpt = Cin / 64;
-  out->nchunks = 4 * cpt;
+  out->nchunks = 3 * 4 * cpt;  // three passes: (x_hi, W_hi), (x_lo, W_hi), (x_hi, W_lo)
   out->N = Cout;
   out->macs_per_row = (double)Cout * Cin * 4;  // per OUTPUT pixel: 2x2 taps
   std::vector<__half> tmp((size_t)4 * out->nchunks * Cout * 64);
   for (int z = 0; z < 4; ++z) {
     const int py = z >> 1, px = z & 1;
     int q = 0;
-    for (int ty = 0; ty < 2; ++ty)
-      for (int tx = 0; tx < 2; ++tx)
-        for (int cc = 0; cc < cpt; ++cc, ++q) {
-          const int ky = 3 - 2 * ty - py, kx = 3 - 2 * tx - px;
-          for (int o = 0; o < Cout; ++o)
-            for (int k = 0; k < 64; ++k) {
-              const int c = cc * 64 + k;
-              tmp[(((size_t)z * out->nchunks + q) * Cout + o) * 64 + k] =
-                  __float2half_rn(w->data[(((size_t)c * Cout + o) * 4 + ky) * 4 + kx]);
-            }
-        }
+    for (int pass = 0; pass < 3; ++pass)
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx)
+          for (int cc = 0; cc < cpt; ++cc, ++q) {
+            const int ky = 3 - 2 * ty - py, kx = 3 - 2 * tx - px;
+            for (int o = 0; o < Cout; ++o)
+              for (int k = 0; k < 64; ++k) {
+                const int c = cc * 64 + k;
+                const float v = w->data[(((size_t)c * Cout + o) * 4 + ky) * 4 + kx];
+                __half hv = __float2half_rn(v);
+                if (pass == 2) hv = __float2half_rn(v - __half2float(hv));
+                tmp[(((size_t)z * out->nchunks + q) * Cout + o) * 64 + k] = hv;
+              }
+          }
   }
   out->w = e->blob.reserve(tmp.size() * 2);
   memcpy(e->blob.at<__half>(out->w), tmp.data(), tmp.size() * 2);
@@ -370,8 +390,9 @@ int pack_ln(cdc_engine* e, const std::string& key, int C, size_t* g, size_t* b) 
 }
 
 int pack_resnet(cdc_engine* e, const std::string& p, int cin, int cout, int k1,
-                const std::vector<SegSpec>& segs1, const std::vector<SegSpec>& segs_res, ResW* out,
-                std::vector<float>* wcat, std::vector<float>* bcat) {
+                const std::vector<SegSpec>& segs1, const std::vector<SegSpec>& segs_res_base,
+                const std::vector<bool>& res_has_lo, ResW* out, std::vector<float>* wcat, std::vector<float>* bcat) {
+  const std::vector<SegSpec> segs_res = three_pass(segs_res_base, res_has_lo);
   int rc;
   out->cin = cin;
   out->cout = cout;
@@ -480,21 +501,40 @@ struct Builder {
   template <typename T>
   T* ws(size_t off) { return reinterpret_cast<T*>(pl->ws + off); }  // valid arithmetic even for ws == nullptr (dry run)
 
-  Act new_act(int C, int h, int w) {
+  Act new_act(int C, int h, int w, bool with_lo = false) {
     Act a;
     a.C = C; a.H = h; a.W = w;
     a.bytes = (size_t)B * h * w * C * 2;
     a.off = arena_base + arena.alloc(a.bytes);
+    if (with_lo) a.off_lo = arena_base + arena.alloc(a.bytes);
     return a;
   }
-  void drop(const Act& a) { arena.release(a.off - arena_base, a.bytes); }
+  void drop(const Act& a) {
+    arena.release(a.off - arena_base, a.bytes);
+    if (a.off_lo) arena.release(a.off_lo - arena_base, a.bytes);
+  }
+  template <typename T>
+  T* lo_ptr(const Act& a) { return a.off_lo ? ws<T>(a.off_lo) : nullptr; }
   size_t raw_alloc(size_t bytes) { return arena_base + arena.alloc(bytes); }
   void raw_free(size_t off, size_t bytes) { arena.release(off - arena_base, bytes); }
 
   struct SegIn {
     Act a;
     int kh, kw, dy0, dx0;
+    bool lo = false;  // read the compensation tensor of `a`
   };
+  // mirror of three_pass() on the activation side: (x_hi, W_hi)..., (x_lo, W_hi) for sources that have lo, (x_hi, W_lo)...
+  static std::vector<SegIn> three_pass_in(const std::vector<SegIn>& base) {
+    std::vector<SegIn> out = base;
+    for (const SegIn& s : base)
+      if (s.a.off_lo) {
+        SegIn t = s;
+        t.lo = true;
+        out.push_back(t);
+      }
+    for (const SegIn& s : base) out.push_back(s);
+    return out;
+  }
 
   // generic conv op. stride / phases describe resampling; epi selects the fused epilogue.
   Op& conv(const std::string& name, const std::vector<SegIn>& segs, const ConvW& w, int epi, const Act& out,
@@ -507,7 +547,7 @@ struct Builder {
     p.nseg = (int)segs.size();
     int total = 0;
     for (int i = 0; i < p.nseg; ++i) {
-      p.seg[i].src = ws<__half>(segs[i].a.off);
+      p.seg[i].src = ws<__half>(segs[i].lo ? segs[i].a.off_lo : segs[i].a.off);
       p.seg[i].C = segs[i].a.C;
       p.seg[i].kh = segs[i].kh;
       p.seg[i].kw = segs[i].kw;
@@ -530,6 +570,7 @@ struct Builder {
     p.phases = phases;
     p.w_phase_stride = (long long)total * w.N * 64;
     p.out = ws<__half>(out.off);
+    p.out_lo = lo_ptr<__half>(out);
     p.out_H = out.H;
     p.out_W = out.W;
     p.out_sy = phases ? 2 : 1;
@@ -560,11 +601,11 @@ struct Builder {
     Act r;
     bool own_r = false;
     if (w.has_res) {
-      r = new_act(w.cout, h, wd);
+      r = new_act(w.cout, h, wd, true);
       own_r = true;
-      conv(name + "res_conv", segs_res, w.res, EPI_BIAS, r, 1, 0);
+      conv(name + "res_conv", three_pass_in(segs_res), w.res, EPI_BIAS, r, 1, 0);
     }
-    Act out = new_act(w.cout, h, wd);
+    Act out = new_act(w.cout, h, wd, true);
     {
       std::vector<SegIn> s2 = {{h1, 3, 3, -1, -1}};
       Op& op = conv(name + "block2", s2, w.b2.conv, EPI_LN_RES, out, 1, 0);
@@ -572,13 +613,17 @@ struct Builder {
       op.conv.ln_b = dptr<float>(e, w.b2.b);
       if (w.has_res) {
         op.conv.res = ws<__half>(r.off);
+        op.conv.res_lo = lo_ptr<__half>(r);
         op.conv.res_C0 = w.cout;
         op.conv.res2 = nullptr;
+        op.conv.res2_lo = nullptr;
       } else {
         // identity residual: the (possibly concatenated) block input itself
         op.conv.res = ws<__half>(segs_res[0].a.off);
+        op.conv.res_lo = lo_ptr<__half>(segs_res[0].a);
         op.conv.res_C0 = segs_res[0].a.C;
         op.conv.res2 = segs_res.size() > 1 ? ws<__half>(segs_res[1].a.off) : nullptr;
+        op.conv.res2_lo = segs_res.size() > 1 ? lo_ptr<__half>(segs_res[1].a) : nullptr;
       }
       op.conv.stats_out = stats_out;
     }
@@ -661,7 +706,7 @@ struct Builder {
       op.grid = dim3(C, B, 1);
     }
     raw_free(Mf, cc_b);
-    Act out = new_act(C, x.H, x.W);
+    Act out = new_act(C, x.H, x.W, true);
     {
       ConvW cw;
       cw.w = 0; cw.bias = 0; cw.N = C; cw.nchunks = cb; cw.macs_per_row = 0;
@@ -677,8 +722,10 @@ struct Builder {
       p.aff_c = ws<float>(cm);
       p.aff_group_stride = C;
       p.res = ws<__half>(x.off);
+      p.res_lo = lo_ptr<__half>(x);
       p.res_C0 = C;
       p.res2 = nullptr;
+      p.res2_lo = nullptr;
       p.bias = nullptr;
       op.grid = dim3(B * ((N + op.bm - 1) / op.bm), C / op.bn, 1);
       op.flops = 0;
@@ -750,9 +797,9 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.w_rows_per_phase = c.total_chunks * N;
   t.w_rows_per_image = c.groups > 1 ? c.total_chunks * N : 0;
   t.epi = op.epi;
-  t.out = c.out; t.out_H = c.out_H; t.out_W = c.out_W; t.out_sy = c.out_sy; t.out_sx = c.out_sx;
+  t.out = c.out; t.out_lo = c.out_lo; t.out_H = c.out_H; t.out_W = c.out_W; t.out_sy = c.out_sy; t.out_sx = c.out_sx;
   t.bias = c.bias; t.ln_g = c.ln_g; t.ln_b = c.ln_b; t.shift = c.shift; t.shift_stride = c.shift_stride;
-  t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2;
+  t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2; t.res_lo = c.res_lo; t.res2_lo = c.res2_lo;
   t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
   op.tcp = t;
   op.tc_smem = tc_smem_bytes(N, t.stages);
@@ -767,19 +814,19 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     cuuint64_t gstr[3] = {Cs * 2, (cuuint64_t)w * Cs * 2, (cuuint64_t)h * w * Cs * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)t.TW, (cuuint32_t)t.TH, (cuuint32_t)t.TB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&op.maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)c.seg[i].src, gdim, gstr, box, estr,
+    CUresult r = enc(&op.maps.a[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)c.seg[i].src, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(A, op %s, seg %d) failed: %d", op.name.c_str(), i, (int)r);
   }
-  for (int i = c.nseg; i < 3; ++i) op.maps[i] = op.maps[0];
+  for (int i = c.nseg; i < kMaxSeg; ++i) op.maps.a[i] = op.maps.a[0];
   {
     const cuuint64_t rows = (cuuint64_t)(c.groups > 1 ? B : t.phases) * c.total_chunks * N;
     cuuint64_t gdim[2] = {64, rows};
     cuuint64_t gstr[1] = {128};
     cuuint32_t box[2] = {64, (cuuint32_t)t.n_piece};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&op.maps[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)c.W, gdim, gstr, box, estr,
+    CUresult r = enc(&op.maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)c.W, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(B, op %s) failed: %d", op.name.c_str(), (int)r);
@@ -872,9 +919,9 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     bd.drop(bq);
     skips.push_back(c);
     if (lv.has_resample) {
-      Act d = bd.new_act(lv.cout, h / 2, w / 2);
+      Act d = bd.new_act(lv.cout, h / 2, w / 2, true);
       std::vector<Builder::SegIn> sd = {{c, 3, 3, -1, -1}};
-      bd.conv(p + "3.down", sd, lv.resample, EPI_BIAS, d, 2, 0);
+      bd.conv(p + "3.down", Builder::three_pass_in(sd), lv.resample, EPI_BIAS, d, 2, 0);
       x = d;
       if (l == 0) { bd.drop(c); }  // the level-0 skip is never consumed (unet.py:102 vs :113)
     } else {
@@ -914,9 +961,9 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     bd.drop(a);
     Act c = bd.attention(p + "2.", bq, st, so, sb, lv.attn);
     bd.drop(bq);
-    Act u = bd.new_act(lv.cout, h * 2, w * 2);
+    Act u = bd.new_act(lv.cout, h * 2, w * 2, true);
     std::vector<Builder::SegIn> su = {{c, 2, 2, 0, 0}};
-    bd.conv(p + "3.up", su, lv.resample, EPI_BIAS, u, 1, 4);
+    bd.conv(p + "3.up", Builder::three_pass_in(su), lv.resample, EPI_BIAS, u, 1, 4);
     bd.drop(c);
     x = u;
   }
@@ -931,6 +978,7 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     pl->final_op = (int)pl->ops.size() - 1;
     // stash input pointer in conv.seg[0].src for the launcher
     op.conv.seg[0].src = bd.ws<__half>(x.off);
+    op.conv.seg[1].src = bd.lo_ptr<__half>(x);
   }
   bd.drop(x);
   pl->total_bytes = bd.arena_base + bd.arena.peak;
@@ -994,8 +1042,7 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
       }
       case OP_CONV: {
         if (op.use_tc) {
-          igemm_tc_kernel<<<op.tc_grid, kTcThreads, op.tc_smem, st>>>(op.maps[0], op.maps[1], op.maps[2], op.maps[3],
-                                                                      op.tcp);
+          igemm_tc_kernel<<<op.tc_grid, kTcThreads, op.tc_smem, st>>>(op.maps, op.tcp);
           break;
         }
         cudaError_t err = launch_igemm(op, st);
@@ -1022,6 +1069,7 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
       case OP_FINAL: {
         FinalParams fp{};
         fp.in = op.conv.seg[0].src;
+        fp.in_lo = op.conv.seg[1].src;
         fp.ln_g = dptr<float>(e, e->f_g);
         fp.ln_b = dptr<float>(e, e->f_b);
         fp.Wf = dptr<__half>(e, e->f_w);
@@ -1223,22 +1271,25 @@ int cdc_engine_finalize(cdc_engine* e) {
         sr.push_back({cc, 1, 1, 0, cx, 0});
       }
     }
-    if ((rc = pack_resnet(e, p + "0.", cin, cout, l == 0 ? 7 : 3, s1, sr, &lv.rb0, &wcat, &bcat))) return rc;
+    // compensation ("lo") halves exist for trunk activations only: not for the packed input / context maps
+    std::vector<bool> sr_lo(sr.size(), false);
+    if (l > 0) sr_lo[0] = true;
+    if ((rc = pack_resnet(e, p + "0.", cin, cout, l == 0 ? 7 : 3, s1, sr, sr_lo, &lv.rb0, &wcat, &bcat))) return rc;
     std::vector<SegSpec> s2 = {{cout, 3, 3, 0, 0, 0}}, sr2 = {{cout, 1, 1, 0, 0, 0}};
-    if ((rc = pack_resnet(e, p + "1.", cout, cout, 3, s2, sr2, &lv.rb1, &wcat, &bcat))) return rc;
+    if ((rc = pack_resnet(e, p + "1.", cout, cout, 3, s2, sr2, {true}, &lv.rb1, &wcat, &bcat))) return rc;
     if ((rc = pack_attn(e, p + "2.", cout, &lv.attn))) return rc;
     lv.has_resample = !last;
     if (!last) {
-      std::vector<SegSpec> sd = {{cout, 3, 3, 0, 0, 0}};
+      std::vector<SegSpec> sd = three_pass({{cout, 3, 3, 0, 0, 0}}, {true});
       if ((rc = pack_conv(e, p + "3.conv", cout, cout, 3, 3, sd, true, &lv.resample))) return rc;
     }
   }
   {
     const int c = e->dims[L];
     std::vector<SegSpec> s = {{c, 3, 3, 0, 0, 0}}, sr = {{c, 1, 1, 0, 0, 0}};
-    if ((rc = pack_resnet(e, "mid_block1.", c, c, 3, s, sr, &e->mid1, &wcat, &bcat))) return rc;
+    if ((rc = pack_resnet(e, "mid_block1.", c, c, 3, s, sr, {true}, &e->mid1, &wcat, &bcat))) return rc;
     if ((rc = pack_attn(e, "mid_attn.", c, &e->mid_attn))) return rc;
-    if ((rc = pack_resnet(e, "mid_block2.", c, c, 3, s, sr, &e->mid2, &wcat, &bcat))) return rc;
+    if ((rc = pack_resnet(e, "mid_block2.", c, c, 3, s, sr, {true}, &e->mid2, &wcat, &bcat))) return rc;
   }
   for (int l = 0; l < L - 1; ++l) {
     Level& lv = e->ups[l];
@@ -1247,9 +1298,9 @@ int cdc_engine_finalize(cdc_engine* e) {
     const std::string p = "ups." + std::to_string(l) + ".";
     std::vector<SegSpec> s1 = {{dim_out, 3, 3, 0, 0, 0}, {dim_out, 3, 3, 0, dim_out, 0}};
     std::vector<SegSpec> sr = {{dim_out, 1, 1, 0, 0, 0}, {dim_out, 1, 1, 0, dim_out, 0}};
-    if ((rc = pack_resnet(e, p + "0.", 2 * dim_out, dim_in, 3, s1, sr, &lv.rb0, &wcat, &bcat))) return rc;
+    if ((rc = pack_resnet(e, p + "0.", 2 * dim_out, dim_in, 3, s1, sr, {true, true}, &lv.rb0, &wcat, &bcat))) return rc;
     std::vector<SegSpec> s2 = {{dim_in, 3, 3, 0, 0, 0}}, sr2 = {{dim_in, 1, 1, 0, 0, 0}};
-    if ((rc = pack_resnet(e, p + "1.", dim_in, dim_in, 3, s2, sr2, &lv.rb1, &wcat, &bcat))) return rc;
+    if ((rc = pack_resnet(e, p + "1.", dim_in, dim_in, 3, s2, sr2, {true}, &lv.rb1, &wcat, &bcat))) return rc;
     if ((rc = pack_attn(e, p + "2.", dim_in, &lv.attn))) return rc;
     lv.has_resample = true;
     if ((rc = pack_convT(e, p + "3.conv", dim_in, dim_in, &lv.resample))) return rc;

@@ -16,7 +16,7 @@
 
 namespace cdc {
 
-constexpr int kMaxSeg = 3;
+constexpr int kMaxSeg = 6;
 enum EpiKind { EPI_BIAS = 0, EPI_LN_SHIFT = 1, EPI_LN_RES = 2, EPI_AFFINE = 3 };
 
 struct ConvSeg {
@@ -42,6 +42,7 @@ struct ConvParams {
   int phases;            // 4 => blockIdx.z is the transposed-conv output phase (py,px)
   long long w_phase_stride;
   __half* out;           // NHWC fp16 [B, out_H, out_W, Ntot]
+  __half* out_lo;        // optional compensation tensor: fp16(value - fp16(value)) ("trunk" activations)
   int out_H, out_W, out_sy, out_sx;
   const float* bias;     // [Ntot] or null
   const float* ln_g;     // LayerNorm affine [Ntot]
@@ -51,6 +52,8 @@ struct ConvParams {
   const __half* res;     // residual, same pixel indexing as out, or null: channels [0,res_C0) ...
   int res_C0;            //   ... and channels [res_C0,Ntot) from res2 (identity residual of a torch.cat input)
   const __half* res2;
+  const __half* res_lo;  // compensation halves of res / res2 (null when the residual source has none)
+  const __half* res2_lo;
   const float2* stats_in;  // EPI_AFFINE: (mean, rstd) per pixel
   const float* aff_u;      // EPI_AFFINE: [groups][Ntot]
   const float* aff_c;
@@ -58,9 +61,38 @@ struct ConvParams {
   float2* stats_out;     // optional: LayerNorm stats of the stored output rows
 };
 
-__device__ __forceinline__ const __half* res_ptr(const ConvParams& p, long long pix, int col) {
-  if (col < p.res_C0) return p.res + (size_t)pix * p.res_C0 + col;
-  return p.res2 + (size_t)pix * (p.Ntot - p.res_C0) + (col - p.res_C0);
+// residual (hi + optional lo) for channels col, col+1 of output pixel pix
+template <class P>
+__device__ __forceinline__ float2 load_res2(const P& p, long long pix, int col) {
+  const __half* hi;
+  const __half* lo;
+  if (col < p.res_C0) {
+    const size_t o = (size_t)pix * p.res_C0 + col;
+    hi = p.res + o;
+    lo = p.res_lo ? p.res_lo + o : nullptr;
+  } else {
+    const size_t o = (size_t)pix * (p.Ntot - p.res_C0) + (col - p.res_C0);
+    hi = p.res2 + o;
+    lo = p.res2_lo ? p.res2_lo + o : nullptr;
+  }
+  float2 r = unpack_half2(*reinterpret_cast<const uint32_t*>(hi));
+  if (lo) {
+    const float2 l = unpack_half2(*reinterpret_cast<const uint32_t*>(lo));
+    r.x += l.x;
+    r.y += l.y;
+  }
+  return r;
+}
+// store v0,v1 as fp16 (+ the rounding remainder into the compensation tensor); returns the stored hi halves
+template <class P>
+__device__ __forceinline__ uint32_t store_out2(const P& p, size_t off, float v0, float v1) {
+  const uint32_t hv = pack_half2(v0, v1);
+  *reinterpret_cast<uint32_t*>(p.out + off) = hv;
+  if (p.out_lo) {
+    const float2 q = unpack_half2(hv);
+    *reinterpret_cast<uint32_t*>(p.out_lo + off) = pack_half2(v0 - q.x, v1 - q.y);
+  }
+  return hv;
 }
 
 template <int BM, int BN>
@@ -261,11 +293,11 @@ __global__ void __launch_bounds__(256) igemm_hmma_kernel(const ConvParams p) {
             v1 += p.bias[col + 1];
           }
           if (p.res) {
-            const float2 rr = unpack_half2(*reinterpret_cast<const uint32_t*>(res_ptr(p, out_pix[mt][h], col)));
+            const float2 rr = load_res2(p, out_pix[mt][h], col);
             v0 += rr.x;
             v1 += rr.y;
           }
-          *reinterpret_cast<uint32_t*>(p.out + base + col) = pack_half2(v0, v1);
+          store_out2(p, base + col, v0, v1);
         }
       }
     return;
@@ -354,12 +386,11 @@ __global__ void __launch_bounds__(256) igemm_hmma_kernel(const ConvParams p) {
             v1 += shift[col + 1];
           }
         } else if (valid && p.res) {
-          const float2 rr = unpack_half2(*reinterpret_cast<const uint32_t*>(res_ptr(p, out_pix[mt][h], col)));
+          const float2 rr = load_res2(p, out_pix[mt][h], col);
           v0 += rr.x;
           v1 += rr.y;
         }
-        const uint32_t hv = pack_half2(v0, v1);
-        if (valid) *reinterpret_cast<uint32_t*>(p.out + base + col) = hv;
+        const uint32_t hv = valid ? store_out2(p, base + col, v0, v1) : pack_half2(v0, v1);
         if (EPI == EPI_LN_RES) {
           const float2 q = unpack_half2(hv);  // statistics of what the consumer will read
           osum[mt][h] += q.x + q.y;

@@ -46,6 +46,7 @@ struct TcConvParams {
   int w_rows_per_image;      // per-image weights (attention): rows between images, else 0
   int epi;
   __half* out;               // NHWC fp16 [B, out_H, out_W, Ntot]
+  __half* out_lo;            // optional compensation tensor (see ConvParams)
   int out_H, out_W, out_sy, out_sx;
   const float* bias;
   const float* ln_g;
@@ -55,15 +56,64 @@ struct TcConvParams {
   const __half* res;
   int res_C0;
   const __half* res2;
+  const __half* res_lo;
+  const __half* res2_lo;
   const float2* stats_in;
   const float* aff_u;        // [B][Ntot] (per image)
   const float* aff_c;
   float2* stats_out;
 };
 
-__device__ __forceinline__ const __half* res_ptr_tc(const TcConvParams& p, long long pix, int col) {
-  if (col < p.res_C0) return p.res + (size_t)pix * p.res_C0 + col;
-  return p.res2 + (size_t)pix * (p.Ntot - p.res_C0) + (col - p.res_C0);
+struct TcMaps {
+  CUtensorMap a[kMaxSeg];
+  CUtensorMap b;
+};
+
+// o[0..8) += residual channels [col, col+8) of pixel pix (hi + optional lo)
+__device__ __forceinline__ void add_res8(const TcConvParams& p, long long pix, int col, float (&o)[8]) {
+  const __half* hi;
+  const __half* lo;
+  if (col < p.res_C0) {
+    const size_t off = (size_t)pix * p.res_C0 + col;
+    hi = p.res + off;
+    lo = p.res_lo ? p.res_lo + off : nullptr;
+  } else {
+    const size_t off = (size_t)pix * (p.Ntot - p.res_C0) + (col - p.res_C0);
+    hi = p.res2 + off;
+    lo = p.res2_lo ? p.res2_lo + off : nullptr;
+  }
+  uint4 rr = *reinterpret_cast<const uint4*>(hi);
+  float2 f;
+  f = unpack_half2(rr.x); o[0] += f.x; o[1] += f.y;
+  f = unpack_half2(rr.y); o[2] += f.x; o[3] += f.y;
+  f = unpack_half2(rr.z); o[4] += f.x; o[5] += f.y;
+  f = unpack_half2(rr.w); o[6] += f.x; o[7] += f.y;
+  if (lo) {
+    rr = *reinterpret_cast<const uint4*>(lo);
+    f = unpack_half2(rr.x); o[0] += f.x; o[1] += f.y;
+    f = unpack_half2(rr.y); o[2] += f.x; o[3] += f.y;
+    f = unpack_half2(rr.z); o[4] += f.x; o[5] += f.y;
+    f = unpack_half2(rr.w); o[6] += f.x; o[7] += f.y;
+  }
+}
+// store 8 channels as fp16 (+ rounding remainders into out_lo); returns the stored hi halves
+__device__ __forceinline__ uint4 store_out8(const TcConvParams& p, size_t off, const float (&o)[8]) {
+  uint4 w;
+  w.x = pack_half2(o[0], o[1]);
+  w.y = pack_half2(o[2], o[3]);
+  w.z = pack_half2(o[4], o[5]);
+  w.w = pack_half2(o[6], o[7]);
+  *reinterpret_cast<uint4*>(p.out + off) = w;
+  if (p.out_lo) {
+    uint4 l;
+    float2 f;
+    f = unpack_half2(w.x); l.x = pack_half2(o[0] - f.x, o[1] - f.y);
+    f = unpack_half2(w.y); l.y = pack_half2(o[2] - f.x, o[3] - f.y);
+    f = unpack_half2(w.z); l.z = pack_half2(o[4] - f.x, o[5] - f.y);
+    f = unpack_half2(w.w); l.w = pack_half2(o[6] - f.x, o[7] - f.y);
+    *reinterpret_cast<uint4*>(p.out_lo + off) = l;
+  }
+  return w;
 }
 
 namespace tc {
@@ -173,9 +223,7 @@ __host__ __device__ inline int tc_smem_bytes(int Ntot, int stages) {
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
-                const TcConvParams p) {
+igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -196,10 +244,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   while (tmem_cols < p.nbuf * N) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    tc::prefetch_tmap(&mapA0);
-    if (p.nseg > 1) tc::prefetch_tmap(&mapA1);
-    if (p.nseg > 2) tc::prefetch_tmap(&mapA2);
-    tc::prefetch_tmap(&mapB);
+    for (int i = 0; i < p.nseg; ++i) tc::prefetch_tmap(&maps.a[i]);
+    tc::prefetch_tmap(&maps.b);
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(bar_full + 8 * s, 1);
       tc::mbar_init(bar_empty + 8 * s, 1);
@@ -246,7 +292,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         int q = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const TcSeg sg = p.seg[s];
-          const CUtensorMap* mA = s == 0 ? &mapA0 : (s == 1 ? &mapA1 : &mapA2);
+          const CUtensorMap* mA = &maps.a[s];
           for (int ky = 0; ky < sg.kh; ++ky)
             for (int kx = 0; kx < sg.kw; ++kx)
               for (int cc = 0; cc < sg.cpt; ++cc, ++q) {
@@ -257,7 +303,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 tc::mbar_expect_tx(full, (uint32_t)stage_bytes);
                 tc::tma_load_4d(sA, mA, full, cc * 64, x0 + kx + sg.dx0 + dxp, y0 + ky + sg.dy0 + dyp, b0);
                 for (int pc = 0; pc < p.n_split; ++pc)
-                  tc::tma_load_2d(sB + pc * p.n_piece * 128, &mapB, full, 0, wrow0 + q * N + pc * p.n_piece);
+                  tc::tma_load_2d(sB + pc * p.n_piece * 128, &maps.b, full, 0, wrow0 + q * N + pc * p.n_piece);
                 if (++stage == p.stages) {
                   stage = 0;
                   phase ^= 1;
@@ -320,7 +366,6 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const bool valid = xx < p.W && yy < p.H && bb < p.B;
       const int py = p.phases > 1 ? (ph >> 1) : 0, px = p.phases > 1 ? (ph & 1) : 0;
       const long long opix = ((long long)bb * p.out_H + yy * p.out_sy + py) * p.out_W + xx * p.out_sx + px;
-      __half* orow = p.out + (size_t)(valid ? opix : 0) * N;
 
       tc::mbar_wait(bar_tfull + 8 * buf, use & 1);
       tc::tc_fence_after();
@@ -351,20 +396,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 const float a = __uint_as_float(v[j + k]);
                 o[k] = p.epi == EPI_AFFINE ? rstd * (a - mean * au[c0 + j + k]) + ac[c0 + j + k] : a + s_vec[c0 + j + k];
               }
-              if (p.res) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res_ptr_tc(p, opix, c0 + j));
-                float2 f;
-                f = unpack_half2(rr.x); o[0] += f.x; o[1] += f.y;
-                f = unpack_half2(rr.y); o[2] += f.x; o[3] += f.y;
-                f = unpack_half2(rr.z); o[4] += f.x; o[5] += f.y;
-                f = unpack_half2(rr.w); o[6] += f.x; o[7] += f.y;
-              }
-              uint4 w;
-              w.x = pack_half2(o[0], o[1]);
-              w.y = pack_half2(o[2], o[3]);
-              w.z = pack_half2(o[4], o[5]);
-              w.w = pack_half2(o[6], o[7]);
-              *reinterpret_cast<uint4*>(orow + c0 + j) = w;
+              if (p.res) add_res8(p, opix, c0 + j, o);
+              store_out8(p, (size_t)opix * N + c0 + j, o);
             }
           }
         }
@@ -402,20 +435,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 o[k] = fmaxf(y, 0.f);
                 if (shift) o[k] += shift[c];
               }
-              if (p.epi == EPI_LN_RES && p.res) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(res_ptr_tc(p, opix, c0 + j));
-                float2 f;
-                f = unpack_half2(rr.x); o[0] += f.x; o[1] += f.y;
-                f = unpack_half2(rr.y); o[2] += f.x; o[3] += f.y;
-                f = unpack_half2(rr.z); o[4] += f.x; o[5] += f.y;
-                f = unpack_half2(rr.w); o[6] += f.x; o[7] += f.y;
-              }
-              uint4 w;
-              w.x = pack_half2(o[0], o[1]);
-              w.y = pack_half2(o[2], o[3]);
-              w.z = pack_half2(o[4], o[5]);
-              w.w = pack_half2(o[6], o[7]);
-              *reinterpret_cast<uint4*>(orow + c0 + j) = w;
+              if (p.epi == EPI_LN_RES && p.res) add_res8(p, opix, c0 + j, o);
+              const uint4 w = store_out8(p, (size_t)opix * N + c0 + j, o);
               if (p.stats_out) {  // statistics of the rounded values the consumer will read
                 float2 f;
                 f = unpack_half2(w.x); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;

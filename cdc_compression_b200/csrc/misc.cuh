@@ -108,6 +108,7 @@ __global__ void advance_step_kernel(int* step_ptr) {
 // ------------------------------------------------------------------------------------------------
 struct FinalParams {
   const __half* in;     // [B,H,W,64] fp16
+  const __half* in_lo;  // optional compensation half of `in`
   const float* ln_g;    // [64]
   const float* ln_b;
   const __half* Wf;     // [8][kFinalWStride] fp16, K index = (ky*7+kx)*64 + c, rows >= channels are zero
@@ -164,6 +165,14 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
         f = unpack_half2(raw.y); v[2] = f.x; v[3] = f.y;
         f = unpack_half2(raw.z); v[4] = f.x; v[5] = f.y;
         f = unpack_half2(raw.w); v[6] = f.x; v[7] = f.y;
+        if (p.in_lo) {
+          const uint4 lo =
+              *reinterpret_cast<const uint4*>(p.in_lo + (((size_t)b * p.H + yy) * p.W + xx) * 64 + j * 8);
+          f = unpack_half2(lo.x); v[0] += f.x; v[1] += f.y;
+          f = unpack_half2(lo.y); v[2] += f.x; v[3] += f.y;
+          f = unpack_half2(lo.z); v[4] += f.x; v[5] += f.y;
+          f = unpack_half2(lo.w); v[6] += f.x; v[7] += f.y;
+        }
       }
       float s = 0.f;
 #pragma unroll

@@ -20,19 +20,28 @@ def r16(x: torch.Tensor) -> torch.Tensor:
     return x.half().to(x.dtype) if ROUND else x
 
 
+def rhl(x: torch.Tensor) -> torch.Tensor:
+    """fp16 value + fp16 rounding remainder: how the engine stores "trunk" activations (ResnetBlock / attention /
+    resample outputs) and the weights of the 3-pass trunk convolutions (res_conv, Downsample, Upsample)."""
+    if not ROUND:
+        return x
+    hi = x.half().to(x.dtype)
+    return hi + (x - hi).half().to(x.dtype)
+
+
 def _ln_stats(x, eps=1e-5):
     var = x.var(dim=1, unbiased=False, keepdim=True)
     mean = x.mean(dim=1, keepdim=True)
     return mean, 1.0 / (var + eps).sqrt()
 
 
-def _block(sd, p, x16, post):
-    """x16 already fp16-rounded.  conv (fp16 w, wide accum) + bias -> LN -> ReLU -> post -> fp16."""
+def _block(sd, p, x, post, store):
+    """conv on the fp16 half of x (fp16 w, wide accum) + bias -> LN -> ReLU -> post -> store."""
     w = r16(sd[p + "block.0.weight"])
-    y = F.conv2d(x16, w, sd[p + "block.0.bias"], padding=w.shape[-1] // 2)
+    y = F.conv2d(r16(x), w, sd[p + "block.0.bias"], padding=w.shape[-1] // 2)
     mean, rstd = _ln_stats(y)
     y = (y - mean) * rstd * sd[p + "block.1.g"] + sd[p + "block.1.b"]
-    return r16(post(F.relu(y)))
+    return store(post(F.relu(y)))
 
 
 TAPS = None  # set to a dict to record per-op outputs under the engine's op names
@@ -49,12 +58,13 @@ def _resnet(sd, p, x16, temb):
         shift = F.linear(F.leaky_relu(temb, 0.2), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])[:, :, None, None]
     else:
         shift = 0.0
-    h = _tap(p + "block1", _block(sd, p + "block1.", x16, lambda v: v + shift))
+    h = _tap(p + "block1", _block(sd, p + "block1.", x16, lambda v: v + shift, r16))
     if (p + "res_conv.weight") in sd:
-        r = _tap(p + "res_conv", r16(F.conv2d(x16, r16(sd[p + "res_conv.weight"]), sd[p + "res_conv.bias"])))
+        # 3-pass: x_hi W_hi + x_lo W_hi + x_hi W_lo  ~  (hi+lo)(W_hi+W_lo)
+        r = _tap(p + "res_conv", rhl(F.conv2d(x16, rhl(sd[p + "res_conv.weight"]), sd[p + "res_conv.bias"])))
     else:
         r = x16
-    return _tap(p + "block2", _block(sd, p + "block2.", h, lambda v: v + r))
+    return _tap(p + "block2", _block(sd, p + "block2.", h, lambda v: v + r, rhl))
 
 
 def _attn(sd, p, x16):
@@ -66,7 +76,9 @@ def _attn(sd, p, x16):
     wq, wkv = wqkv[:c], wqkv[c:]
     wo = sd[p + "fn.fn.to_out.weight"].reshape(c, c)
     bo = sd[p + "fn.fn.to_out.bias"]
-    mean, rstd = _ln_stats(x16)                      # stats of the stored (rounded) tensor
+    xres = x16.reshape(b, c, n)                      # residual: hi + lo
+    x16 = r16(x16)                                   # GEMM operand and LayerNorm statistics: the fp16 half
+    mean, rstd = _ln_stats(x16)
     xf = x16.reshape(b, c, n)
     mean, rstd = mean.reshape(b, 1, n), rstd.reshape(b, 1, n)
     # K,V = rstd*(Wg x - mean*u) + c   (LayerNorm folded into the GEMM epilogue)
@@ -84,8 +96,8 @@ def _attn(sd, p, x16):
     mg = r16(mb * g[None])
     um = mg.sum(dim=2)
     cm = torch.einsum("boc,c->bo", mb, bl) + bo[None]
-    out = rstd * (torch.einsum("boc,bcn->bon", mg, xf) - mean * um[:, :, None]) + cm[:, :, None] + xf
-    return _tap(p + "out", r16(out.reshape(b, c, h, w)))
+    out = rstd * (torch.einsum("boc,bcn->bon", mg, xf) - mean * um[:, :, None]) + cm[:, :, None] + xres
+    return _tap(p + "out", rhl(out.reshape(b, c, h, w)))
 
 
 def unet_forward_emulated(sd, x, time, context: Sequence[torch.Tensor]):
@@ -105,7 +117,7 @@ def unet_forward_emulated(sd, x, time, context: Sequence[torch.Tensor]):
         x = _attn(sd, p + "2.", x)
         skips.append(x)
         if (p + "3.conv.weight") in sd:
-            x = _tap(p + "3.down", r16(F.conv2d(x, r16(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1)))
+            x = _tap(p + "3.down", rhl(F.conv2d(x, rhl(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1)))
     x = _resnet(sd, "mid_block1.", x, temb)
     x = _attn(sd, "mid_attn.", x)
     x = _resnet(sd, "mid_block2.", x, temb)
@@ -116,7 +128,7 @@ def unet_forward_emulated(sd, x, time, context: Sequence[torch.Tensor]):
         x = _resnet(sd, p + "1.", x, temb)
         x = _attn(sd, p + "2.", x)
         if (p + "3.conv.weight") in sd:
-            x = _tap(p + "3.up", r16(F.conv_transpose2d(x, r16(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1)))
+            x = _tap(p + "3.up", rhl(F.conv_transpose2d(x, rhl(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"], stride=2, padding=1)))
     _tap("final_conv", x)
     mean, rstd = _ln_stats(x)
     xn = r16((x - mean) * rstd * sd["final_conv.0.g"] + sd["final_conv.0.b"])

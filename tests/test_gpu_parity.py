@@ -18,7 +18,7 @@ from golden.make_golden import CASES, LOOPS, case_inputs
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-REL_L2_UNET = 1.5e-3   # measured 1.1-1.25e-3 with single-pass fp16 operands (see DESIGN.md "precision")
+REL_L2_UNET = 1.0e-3   # north_star tolerance; measured 6.2e-4 (eps) / 6.7e-4 (x) with the compensated trunk (DESIGN.md "precision")
 torch.set_grad_enabled(False)
 
 
