@@ -762,8 +762,9 @@ int pow2floor(int v) {
 int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   const ConvParams& c = op.conv;
   op.use_tc = false;
-  if (e->mainloop != 1 || c.stride != 1) return 0;
-  const int B = pl->B, h = c.Hs, w = c.Ws, N = c.Ntot;
+  if (e->mainloop != 1) return 0;
+  // tile space = output pixels (for the transposed-conv phases: the input-resolution pixels of one phase)
+  const int B = pl->B, h = c.Ho, w = c.Wo, N = c.Ntot;
   TcConvParams t{};
   t.TW = std::min(16, pow2floor(w));
   if (c.groups > 1) {  // per-image weights: a tile must stay inside one image
@@ -779,6 +780,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.tiles_y = (h + t.TH - 1) / t.TH;
   t.tiles_b = (B + t.TB - 1) / t.TB;
   t.B = B; t.H = h; t.W = w;
+  t.stride = c.stride;
   t.nseg = c.nseg;
   for (int i = 0; i < c.nseg; ++i) {
     t.seg[i].cpt = c.seg[i].C / 64;
@@ -791,7 +793,9 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.n_split = N > 256 ? 2 : 1;
   t.n_piece = N / t.n_split;
   t.nbuf = (2 * N <= 512) ? 2 : 1;
-  const int budget = 227 * 1024 - 1024 - 5 * 384 * 4 - 256;
+  // N <= 128: two CTAs per SM (2 x 256 TMEM columns, half the shared memory each) double the epilogue warps
+  const int ctas_per_sm = N <= 128 ? 2 : 1;
+  const int budget = (227 * 1024) / ctas_per_sm - 1024 - 5 * 384 * 4 - 256 - (ctas_per_sm > 1 ? 1024 : 0);
   t.stages = std::max(2, std::min(kTcMaxStages, budget / tc_stage_bytes(N)));
   t.phases = c.phases ? 4 : 1;
   t.w_rows_per_phase = c.total_chunks * N;
@@ -803,17 +807,20 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
   op.tcp = t;
   op.tc_smem = tc_smem_bytes(N, t.stages);
-  op.tc_grid = std::min(t.tiles_x * t.tiles_y * t.tiles_b * t.phases, e->num_sms);
+  op.tc_grid = std::min(t.tiles_x * t.tiles_y * t.tiles_b * t.phases, e->num_sms * ctas_per_sm);
   op.use_tc = true;
   if (!pl->ws) return 0;  // dry run: geometry only
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   for (int i = 0; i < c.nseg; ++i) {
     const cuuint64_t Cs = (cuuint64_t)c.seg[i].C;
-    cuuint64_t gdim[4] = {Cs, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
-    cuuint64_t gstr[3] = {Cs * 2, (cuuint64_t)w * Cs * 2, (cuuint64_t)h * w * Cs * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)t.TW, (cuuint32_t)t.TH, (cuuint32_t)t.TB};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint64_t ws_ = (cuuint64_t)c.Ws, hs_ = (cuuint64_t)c.Hs;
+    cuuint64_t gdim[4] = {Cs, ws_, hs_, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {Cs * 2, ws_ * Cs * 2, hs_ * ws_ * Cs * 2};
+    // strided convolution: the box spans stride*T source pixels, of which every stride-th is loaded
+    const cuuint32_t sx = (cuuint32_t)c.stride;
+    cuuint32_t box[4] = {64, (cuuint32_t)t.TW * sx, (cuuint32_t)t.TH * sx, (cuuint32_t)t.TB};
+    cuuint32_t estr[4] = {1, sx, sx, 1};
     CUresult r = enc(&op.maps.a[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)c.seg[i].src, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -33,7 +33,8 @@ struct TcSeg {
 struct TcConvParams {
   int TW, TH, TB;            // tile = TB x TH x TW = 128 pixels
   int tiles_x, tiles_y, tiles_b;
-  int B, H, W;               // tile-space (== source) extents
+  int B, H, W;               // tile-space (output) extents; source pixel = stride * tile pixel + tap offset
+  int stride;
   int nseg;
   TcSeg seg[kMaxSeg];
   int total_chunks;
@@ -222,7 +223,7 @@ __host__ __device__ inline int tc_smem_bytes(int Ntot, int stages) {
   return 1024 /*alignment slack*/ + stages * tc_stage_bytes(Ntot) + 5 * 384 * 4 + 256;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -301,7 +302,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
                 const uint32_t sB = sA + 16384;
                 const uint32_t full = bar_full + 8 * stage;
                 tc::mbar_expect_tx(full, (uint32_t)stage_bytes);
-                tc::tma_load_4d(sA, mA, full, cc * 64, x0 + kx + sg.dx0 + dxp, y0 + ky + sg.dy0 + dyp, b0);
+                tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp, y0 * p.stride + ky + sg.dy0 + dyp, b0);
                 for (int pc = 0; pc < p.n_split; ++pc)
                   tc::tma_load_2d(sB + pc * p.n_piece * 128, &maps.b, full, 0, wrow0 + q * N + pc * p.n_piece);
                 if (++stage == p.stages) {
@@ -352,6 +353,9 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
     // =============================== epilogue (4 warps, one GEMM row per thread) ===============================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // GEMM row == TMEM lane
+    const int lx = row % p.TW, ly = (row / p.TW) % p.TH, lb = row / (p.TW * p.TH);
+    const float inv_n = 1.f / (float)N;
+    int cached_img = -1;                       // image whose affine vectors sit in s_vec[3*384..] (EPI_AFFINE)
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int buf = it % p.nbuf;
@@ -361,11 +365,62 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       const int tb = r / (p.tiles_x * p.tiles_y);
       r -= tb * p.tiles_x * p.tiles_y;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int lx = row % p.TW, ly = (row / p.TW) % p.TH, lb = row / (p.TW * p.TH);
       const int xx = tx * p.TW + lx, yy = ty * p.TH + ly, bb = tb * p.TB + lb;
       const bool valid = xx < p.W && yy < p.H && bb < p.B;
       const int py = p.phases > 1 ? (ph >> 1) : 0, px = p.phases > 1 ? (ph & 1) : 0;
-      const long long opix = ((long long)bb * p.out_H + yy * p.out_sy + py) * p.out_W + xx * p.out_sx + px;
+      const long long opix =
+          valid ? ((long long)bb * p.out_H + yy * p.out_sy + py) * p.out_W + xx * p.out_sx + px : 0;
+      const size_t obase = (size_t)opix * N;
+      const bool has_res = p.res != nullptr && (p.epi != EPI_LN_SHIFT);
+
+      // residual prefetch (hi / lo halves of 32 channels) — issued ahead of the TMEM waits that would expose it
+      uint4 rh[4], rl[4];
+      auto prefetch_res = [&](int c0) {
+        if (!(has_res && valid)) return;
+        const __half* hi;
+        const __half* lo;
+        if (c0 < p.res_C0) {
+          const size_t off = (size_t)opix * p.res_C0 + c0;
+          hi = p.res + off;
+          lo = p.res_lo ? p.res_lo + off : nullptr;
+        } else {
+          const size_t off = (size_t)opix * (N - p.res_C0) + (c0 - p.res_C0);
+          hi = p.res2 + off;
+          lo = p.res2_lo ? p.res2_lo + off : nullptr;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          rh[j] = reinterpret_cast<const uint4*>(hi)[j];
+          rl[j] = lo ? reinterpret_cast<const uint4*>(lo)[j] : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      auto add_res = [&](int j, float (&o)[8]) {  // j = 8-channel group inside the prefetched 32
+        float2 f;
+        f = unpack_half2(rh[j].x); o[0] += f.x; o[1] += f.y;
+        f = unpack_half2(rh[j].y); o[2] += f.x; o[3] += f.y;
+        f = unpack_half2(rh[j].z); o[4] += f.x; o[5] += f.y;
+        f = unpack_half2(rh[j].w); o[6] += f.x; o[7] += f.y;
+        f = unpack_half2(rl[j].x); o[0] += f.x; o[1] += f.y;
+        f = unpack_half2(rl[j].y); o[2] += f.x; o[3] += f.y;
+        f = unpack_half2(rl[j].z); o[4] += f.x; o[5] += f.y;
+        f = unpack_half2(rl[j].w); o[6] += f.x; o[7] += f.y;
+      };
+      prefetch_res(0);
+
+      float2 st = make_float2(0.f, 1.f);
+      if (p.epi == EPI_AFFINE) {
+        if (valid) st = p.stats_in[opix];
+        const int img = tb * p.TB;  // TB == 1 for per-image (attention) weights: one image per tile
+        if (img != cached_img) {    // uniform across the 4 epilogue warps
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = threadIdx.x - 64; i < N; i += 128) {
+            s_vec[3 * 384 + i] = p.aff_u[(size_t)img * N + i];
+            s_vec[4 * 384 + i] = p.aff_c[(size_t)img * N + i];
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          cached_img = img;
+        }
+      }
 
       tc::mbar_wait(bar_tfull + 8 * buf, use & 1);
       tc::tc_fence_after();
@@ -373,33 +428,25 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       uint32_t v[32];
 
       if (p.epi == EPI_BIAS || p.epi == EPI_AFFINE) {
-        float mean = 0.f, rstd = 1.f;
-        const float* au = nullptr;
-        const float* ac = nullptr;
-        if (p.epi == EPI_AFFINE) {
-          if (valid) {
-            const float2 st = p.stats_in[opix];
-            mean = st.x;
-            rstd = st.y;
-          }
-          au = p.aff_u + (size_t)(valid ? bb : 0) * N;
-          ac = p.aff_c + (size_t)(valid ? bb : 0) * N;
-        }
         for (int c0 = 0; c0 < N; c0 += 32) {
           tc::tmem_ld32(taddr + c0, v);
-          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float o[8];
+          for (int j = 0; j < 4; ++j) {
+            float o[8];
+            if (p.epi == EPI_AFFINE) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                const float a = __uint_as_float(v[j + k]);
-                o[k] = p.epi == EPI_AFFINE ? rstd * (a - mean * au[c0 + j + k]) + ac[c0 + j + k] : a + s_vec[c0 + j + k];
+                const int c = c0 + j * 8 + k;
+                o[k] = st.y * (__uint_as_float(v[j * 8 + k]) - st.x * s_vec[3 * 384 + c]) + s_vec[4 * 384 + c];
               }
-              if (p.res) add_res8(p, opix, c0 + j, o);
-              store_out8(p, (size_t)opix * N + c0 + j, o);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(v[j * 8 + k]) + s_vec[c0 + j * 8 + k];
             }
+            if (has_res) add_res(j, o);
+            if (valid) store_out8(p, obase + c0 + j * 8, o);
           }
+          if (c0 + 32 < N) prefetch_res(c0 + 32);
         }
       } else {
         // ---- channel LayerNorm: exact two-pass statistics from the fp32 accumulator ----
@@ -409,7 +456,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]) + s_vec[c0 + j];
         }
-        const float mean = sum / (float)N;
+        const float mean = sum * inv_n;
         float sq = 0.f;
         for (int c0 = 0; c0 < N; c0 += 32) {
           tc::tmem_ld32(taddr + c0, v);
@@ -419,24 +466,33 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
             sq += d * d;
           }
         }
-        const float rstd = 1.f / sqrtf(sq / (float)N + 1e-5f);
-        const float* shift = (p.epi == EPI_LN_SHIFT && p.shift) ? p.shift + (size_t)(valid ? bb : 0) * p.shift_stride : nullptr;
+        const float rstd = 1.f / sqrtf(sq * inv_n + 1e-5f);
+        const float* shift =
+            (p.epi == EPI_LN_SHIFT && p.shift && valid) ? p.shift + (size_t)bb * p.shift_stride : nullptr;
         float osum = 0.f, osq = 0.f;
         for (int c0 = 0; c0 < N; c0 += 32) {
+          float4 sh[8];
+          if (shift) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sh[j] = reinterpret_cast<const float4*>(shift + c0)[j];
+          }
           tc::tmem_ld32(taddr + c0, v);
-          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float o[8];
+          for (int j = 0; j < 4; ++j) {
+            float o[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int c = c0 + j + k;
-                const float y = (__uint_as_float(v[j + k]) + s_vec[c] - mean) * rstd * s_vec[384 + c] + s_vec[768 + c];
-                o[k] = fmaxf(y, 0.f);
-                if (shift) o[k] += shift[c];
-              }
-              if (p.epi == EPI_LN_RES && p.res) add_res8(p, opix, c0 + j, o);
-              const uint4 w = store_out8(p, (size_t)opix * N + c0 + j, o);
+            for (int k = 0; k < 8; ++k) {
+              const int c = c0 + j * 8 + k;
+              const float y = (__uint_as_float(v[j * 8 + k]) + s_vec[c] - mean) * rstd * s_vec[384 + c] + s_vec[768 + c];
+              o[k] = fmaxf(y, 0.f);
+            }
+            if (shift) {
+              o[0] += sh[2 * j].x; o[1] += sh[2 * j].y; o[2] += sh[2 * j].z; o[3] += sh[2 * j].w;
+              o[4] += sh[2 * j + 1].x; o[5] += sh[2 * j + 1].y; o[6] += sh[2 * j + 1].z; o[7] += sh[2 * j + 1].w;
+            }
+            if (has_res) add_res(j, o);
+            if (valid) {
+              const uint4 w = store_out8(p, obase + c0 + j * 8, o);
               if (p.stats_out) {  // statistics of the rounded values the consumer will read
                 float2 f;
                 f = unpack_half2(w.x); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
@@ -446,10 +502,11 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
               }
             }
           }
+          if (c0 + 32 < N) prefetch_res(c0 + 32);
         }
         if (p.stats_out && valid) {
-          const float m = osum / (float)N;
-          const float var = fmaxf(osq / (float)N - m * m, 0.f);
+          const float m = osum * inv_n;
+          const float var = fmaxf(osq * inv_n - m * m, 0.f);
           p.stats_out[opix] = make_float2(m, 1.f / sqrtf(var + 1e-5f));
         }
       }
