@@ -81,7 +81,7 @@ struct Level {
 };
 
 // ---------------------------------------------------------------- plan
-enum OpKind { OP_PACK, OP_CONV, OP_TIME, OP_ATTN_CTX, OP_COMBINE, OP_SGEMM, OP_FINISH, OP_FINAL, OP_ADVANCE };
+enum OpKind { OP_PACK, OP_CONV, OP_TIME, OP_ATTN_CTX, OP_COMBINE, OP_SGEMM, OP_FINISH, OP_FINAL, OP_ADVANCE, OP_LNROWS };
 
 struct Op {
   int kind = 0;
@@ -100,6 +100,7 @@ struct Op {
   TcMaps maps;
   TcConvParams tcp{};
   int tc_grid = 0, tc_smem = 0;
+  LnRowsParams lnr{};   // OP_LNROWS: second half of a sliced convolution
   // debug view of the op's fp16 NHWC output (if any)
   const __half* dbg = nullptr;
   int dC = 0, dH = 0, dW = 0;
@@ -165,6 +166,7 @@ struct Plan {
   std::vector<size_t> ctx_off;     // fp16 NHWC context per level (level 0 of the eps variant: fp32 NCHW copy)
   size_t shifts_off = 0;
   size_t xstate_off = 0;           // fp32 NCHW sampler state the captured graph works on
+  size_t raw_off = 0, raw_bytes = 0;   // fp32 partial tiles of the sliced convolutions (after the arena)
   int pack_op = -1, time_op = -1, final_op = -1;
   double flops = 0;
   // captured step graph
@@ -194,6 +196,7 @@ struct cdc_engine {
   bool debug_no_reuse = false;
   int mainloop = 1;   // 0 = mma.sync kernels, 1 = tcgen05/TMA kernels for stride-1 convolutions (default)
   int num_sms = 148;
+  bool sliced = true;  // CDC_SLICED=0 disables the sliced low-resolution mode (A/B measurements)
   // derived structure
   std::vector<int> dims, cdims;
   bool fold_ctx0 = false;  // small level-0 context folded into the packed input (eps demo)
@@ -490,6 +493,32 @@ cudaError_t launch_igemm(const Op& op, cudaStream_t st) {
   return cudaErrorInvalidValue;
 }
 
+template <int EPI, int OCC>
+cudaError_t launch_tc_t(const Op& op, cudaStream_t st) {
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && !attr_set[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(igemm_tc_kernel<EPI, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024 / OCC);
+    if (err != cudaSuccess) return err;
+    attr_set[dev] = true;
+  }
+  igemm_tc_kernel<EPI, OCC><<<op.tc_grid, kTcThreads, op.tc_smem, st>>>(op.maps, op.tcp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc(const Op& op, cudaStream_t st) {
+  const int occ = op.tcp.Nc <= 128 ? 2 : 1;
+#define CASE(E_)                                                \
+  if (op.tcp.epi == E_) {                                       \
+    return occ == 2 ? launch_tc_t<E_, 2>(op, st) : launch_tc_t<E_, 1>(op, st); \
+  }
+  CASE(EPI_BIAS) CASE(EPI_LN_SHIFT) CASE(EPI_LN_RES) CASE(EPI_AFFINE) CASE(EPI_RAW)
+#undef CASE
+  return cudaErrorInvalidValue;
+}
+
 // ---------------------------------------------------------------- plan builder
 struct Builder {
   cdc_engine* e;
@@ -752,6 +781,8 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+constexpr int kSlicedMaxTiles = 100;  // layers with fewer 128-pixel output tiles run in sliced mode
+
 int pow2floor(int v) {
   int r = 1;
   while (r * 2 <= v) r *= 2;
@@ -790,24 +821,42 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   }
   t.total_chunks = c.total_chunks;
   t.Ntot = N;
-  t.n_split = N > 256 ? 2 : 1;
-  t.n_piece = N / t.n_split;
-  t.nbuf = (2 * N <= 512) ? 2 : 1;
-  // N <= 128: two CTAs per SM (2 x 256 TMEM columns, half the shared memory each) double the epilogue warps
-  const int ctas_per_sm = N <= 128 ? 2 : 1;
+  // Sliced mode for layers that cannot fill the GPU with 128-pixel tiles: 64-column slices x K splits, fp32
+  // partial tiles finished by ln_rows_kernel (see TcConvParams).
+  const int tiles_total = t.tiles_x * t.tiles_y * t.tiles_b * (c.phases ? 4 : 1);
+  t.Nc = N; t.n_slices = 1; t.k_splits = 1;
+  const bool sliceable = e->sliced && c.groups == 1 && op.epi != EPI_AFFINE && tiles_total < kSlicedMaxTiles && N >= 128;
+  if (sliceable) {
+    t.Nc = 64;
+    t.n_slices = N / 64;
+    const int slots = 2 * e->num_sms;
+    t.k_splits = std::max(1, std::min(c.total_chunks / 2, (slots + tiles_total * t.n_slices - 1) / (tiles_total * t.n_slices)));
+  }
+  const int Nc = t.Nc;
+  t.n_split = Nc > 256 ? 2 : 1;
+  t.n_piece = Nc / t.n_split;
+  t.nbuf = (2 * Nc <= 512) ? 2 : 1;
+  // Nc <= 128: two CTAs per SM (2 x 256 TMEM columns, half the shared memory each) double the epilogue warps
+  const int ctas_per_sm = Nc <= 128 ? 2 : 1;
   const int budget = (227 * 1024) / ctas_per_sm - 1024 - 5 * 384 * 4 - 256 - (ctas_per_sm > 1 ? 1024 : 0);
-  t.stages = std::max(2, std::min(kTcMaxStages, budget / tc_stage_bytes(N)));
+  t.stages = std::max(2, std::min(kTcMaxStages, budget / tc_stage_bytes(Nc)));
   t.phases = c.phases ? 4 : 1;
   t.w_rows_per_phase = c.total_chunks * N;
   t.w_rows_per_image = c.groups > 1 ? c.total_chunks * N : 0;
-  t.epi = op.epi;
+  t.epi = sliceable ? EPI_RAW : op.epi;
   t.out = c.out; t.out_lo = c.out_lo; t.out_H = c.out_H; t.out_W = c.out_W; t.out_sy = c.out_sy; t.out_sx = c.out_sx;
   t.bias = c.bias; t.ln_g = c.ln_g; t.ln_b = c.ln_b; t.shift = c.shift; t.shift_stride = c.shift_stride;
   t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2; t.res_lo = c.res_lo; t.res2_lo = c.res2_lo;
   t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
+  op.tc_smem = tc_smem_bytes(Nc, t.stages);
+  op.tc_grid = std::min(tiles_total * t.n_slices * t.k_splits, e->num_sms * ctas_per_sm);
+  if (sliceable) {
+    const long long out_pix = (long long)B * c.out_H * c.out_W;
+    t.raw_split_stride = out_pix * N;
+    t.raw = reinterpret_cast<float*>(pl->ws + pl->raw_off);
+    pl->raw_bytes = std::max(pl->raw_bytes, (size_t)((size_t)t.k_splits * (size_t)out_pix * (size_t)N * 4));
+  }
   op.tcp = t;
-  op.tc_smem = tc_smem_bytes(N, t.stages);
-  op.tc_grid = std::min(t.tiles_x * t.tiles_y * t.tiles_b * t.phases, e->num_sms * ctas_per_sm);
   op.use_tc = true;
   if (!pl->ws) return 0;  // dry run: geometry only
   EncodeTiledFn enc = encode_tiled_fn();
@@ -988,12 +1037,48 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     op.conv.seg[1].src = bd.lo_ptr<__half>(x);
   }
   bd.drop(x);
-  pl->total_bytes = bd.arena_base + bd.arena.peak;
-  for (auto& op : pl->ops)
-    if (op.kind == OP_CONV) {
+  pl->raw_off = (bd.arena_base + bd.arena.peak + 255) & ~size_t(255);
+  pl->raw_bytes = 0;
+  {
+    std::vector<Op> ops2;
+    ops2.reserve(pl->ops.size() + 64);
+    for (auto& op : pl->ops) {
+      if (op.kind != OP_CONV) { ops2.push_back(op); continue; }
       int rc = setup_tc(e, pl, op);
       if (rc) return rc;
+      if (!(op.use_tc && op.tcp.epi == EPI_RAW)) { ops2.push_back(op); continue; }
+      // sliced convolution = raw partial tiles (this op) + row-wise epilogue (next op, keeps the op's name)
+      const ConvParams& c = op.conv;
+      Op fin;
+      fin.kind = OP_LNROWS;
+      fin.name = op.name;
+      fin.dbg = op.dbg; fin.dC = op.dC; fin.dH = op.dH; fin.dW = op.dW;
+      LnRowsParams& q = fin.lnr;
+      q.raw = op.tcp.raw;
+      q.k_splits = op.tcp.k_splits;
+      q.split_stride = op.tcp.raw_split_stride;
+      q.N = c.Ntot; q.Ntot = c.Ntot;
+      q.rows = (long long)pl->B * c.out_H * c.out_W;
+      q.pix_per_image = c.out_H * c.out_W;
+      q.epi = op.epi;
+      q.bias = c.bias; q.ln_g = c.ln_g; q.ln_b = c.ln_b; q.shift = c.shift; q.shift_stride = c.shift_stride;
+      q.res = c.res; q.res_C0 = c.res_C0; q.res2 = c.res2; q.res_lo = c.res_lo; q.res2_lo = c.res2_lo;
+      q.out = c.out; q.out_lo = c.out_lo; q.stats_out = c.stats_out;
+      fin.grid = dim3((unsigned)((q.rows + 7) / 8), 1, 1);
+      op.name += "#partials";
+      op.dbg = nullptr;
+      fin.flops = 0;
+      ops2.push_back(op);
+      ops2.push_back(fin);
     }
+    pl->ops.swap(ops2);
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+      if (pl->ops[i].kind == OP_TIME) pl->time_op = (int)i;
+      if (pl->ops[i].kind == OP_PACK) pl->pack_op = (int)i;
+      if (pl->ops[i].kind == OP_FINAL) pl->final_op = (int)i;
+    }
+  }
+  pl->total_bytes = pl->raw_off + pl->raw_bytes;
   pl->flops = 0;
   for (auto& op : pl->ops) pl->flops += op.flops;
   return 0;
@@ -1049,7 +1134,9 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
       }
       case OP_CONV: {
         if (op.use_tc) {
-          igemm_tc_kernel<<<op.tc_grid, kTcThreads, op.tc_smem, st>>>(op.maps, op.tcp);
+          cudaError_t err = launch_tc(op, st);
+          if (err != cudaSuccess)
+            return fail(e, CDC_ERR_CUDA, "tcgen05 conv launch '%s': %s", op.name.c_str(), cudaGetErrorString(err));
           break;
         }
         cudaError_t err = launch_igemm(op, st);
@@ -1068,6 +1155,9 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
       case OP_SGEMM:
         sgemm_tn_kernel<<<op.grid, 256, 0, st>>>(op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N, op.sg.K, op.sg.sA,
                                                  op.sg.sB, op.sg.sC);
+        break;
+      case OP_LNROWS:
+        ln_rows_kernel<<<op.grid, 256, 0, st>>>(op.lnr);
         break;
       case OP_FINISH:
         attn_finish_kernel<<<op.grid, 128, 0, st>>>(op.fin.Mf, op.fin.g, op.fin.bln, op.fin.bout, op.fin.C, op.fin.Mg,
@@ -1200,7 +1290,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
       cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess)
     return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   e->num_sms = prop.multiProcessorCount;
-  cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   *out = e.release();

@@ -63,7 +63,17 @@ struct TcConvParams {
   const float* aff_u;        // [B][Ntot] (per image)
   const float* aff_c;
   float2* stats_out;
+  // Sliced mode (low-resolution layers: few output tiles, long K, wide N).  The work of one output tile is spread
+  // over n_slices x k_splits CTAs: each computes columns [slice*Nc, +Nc) over a K sub-range and stores its fp32
+  // partial tile to raw[k_split][out_pixel][Ntot]; ln_rows_kernel then sums the K partials in a fixed order and
+  // applies the fused epilogue (deterministic, no atomics).  Nc == Ntot, n_slices == k_splits == 1 otherwise.
+  int Nc;
+  int n_slices, k_splits;
+  float* raw;
+  long long raw_split_stride;
 };
+
+constexpr int EPI_RAW = 4;
 
 struct TcMaps {
   CUtensorMap a[kMaxSeg];
@@ -223,13 +233,15 @@ __host__ __device__ inline int tc_smem_bytes(int Ntot, int stages) {
   return 1024 /*alignment slack*/ + stages * tc_stage_bytes(Ntot) + 5 * 384 * 4 + 256;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 2)
+// EPI: fused epilogue (compile-time, prunes the others); OCC: CTAs per SM the register budget is sized for.
+template <int EPI, int OCC>
+__global__ void __launch_bounds__(kTcThreads, OCC)
 igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int stage_bytes = tc_stage_bytes(p.Ntot);
+  const int stage_bytes = tc_stage_bytes(p.Nc);
   float* s_vec = reinterpret_cast<float*>(smem + p.stages * stage_bytes);  // bias | g | b | (u | c): 5 x 384
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + 5 * 384 * 4);
   // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2]; then the TMEM base address word
@@ -240,7 +252,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kTcMaxStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = p.Ntot;
+  const int N = p.Nc;   // accumulator columns owned by this CTA (== Ntot unless sliced)
   int tmem_cols = 32;
   while (tmem_cols < p.nbuf * N) tmem_cols <<= 1;
 
@@ -275,13 +287,19 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
 
   const int tiles_per_phase = p.tiles_x * p.tiles_y * p.tiles_b;
   const int total_tiles = tiles_per_phase * p.phases;
+  const int units_per_tile = p.n_slices * p.k_splits;
+  const int total_units = total_tiles * units_per_tile;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int t = u / units_per_tile;
+        const int su = u - t * units_per_tile;
+        const int slice = su / p.k_splits, ksp = su - slice * p.k_splits;
+        const int q0 = (ksp * p.total_chunks) / p.k_splits, q1 = ((ksp + 1) * p.total_chunks) / p.k_splits;
         const int ph = t / tiles_per_phase;
         int r = t - ph * tiles_per_phase;
         const int tb = r / (p.tiles_x * p.tiles_y);
@@ -289,7 +307,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB;
         const int dyp = p.phases > 1 ? (ph >> 1) - 1 : 0, dxp = p.phases > 1 ? (ph & 1) - 1 : 0;
-        const int wrow0 = ph * p.w_rows_per_phase + b0 * p.w_rows_per_image;
+        const int wrow0 = ph * p.w_rows_per_phase + b0 * p.w_rows_per_image + slice * N;
         int q = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const TcSeg sg = p.seg[s];
@@ -297,6 +315,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
           for (int ky = 0; ky < sg.kh; ++ky)
             for (int kx = 0; kx < sg.kw; ++kx)
               for (int cc = 0; cc < sg.cpt; ++cc, ++q) {
+                if (q < q0 || q >= q1) continue;
                 tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 const uint32_t sA = base + stage * stage_bytes;
                 const uint32_t sB = sA + 16384;
@@ -304,7 +323,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
                 tc::mbar_expect_tx(full, (uint32_t)stage_bytes);
                 tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp, y0 * p.stride + ky + sg.dy0 + dyp, b0);
                 for (int pc = 0; pc < p.n_split; ++pc)
-                  tc::tma_load_2d(sB + pc * p.n_piece * 128, &maps.b, full, 0, wrow0 + q * N + pc * p.n_piece);
+                  tc::tma_load_2d(sB + pc * p.n_piece * 128, &maps.b, full, 0, wrow0 + q * p.Ntot + pc * p.n_piece);
                 if (++stage == p.stages) {
                   stage = 0;
                   phase ^= 1;
@@ -320,13 +339,15 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+        const int ksp = u % p.k_splits;
+        const int nq = ((ksp + 1) * p.total_chunks) / p.k_splits - (ksp * p.total_chunks) / p.k_splits;
         const int buf = it % p.nbuf;
         const uint32_t use = (uint32_t)(it / p.nbuf);  // how many times this buffer was used before
         tc::mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
-        for (int q = 0; q < p.total_chunks; ++q) {
+        for (int q = 0; q < nq; ++q) {
           tc::mbar_wait(bar_full + 8 * stage, phase);
           tc::tc_fence_after();
           const uint32_t sA = base + stage * stage_bytes;
@@ -357,7 +378,8 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
     const float inv_n = 1.f / (float)N;
     int cached_img = -1;                       // image whose affine vectors sit in s_vec[3*384..] (EPI_AFFINE)
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      const int t = u / units_per_tile;
       const int buf = it % p.nbuf;
       const uint32_t use = (uint32_t)(it / p.nbuf);
       const int ph = t / tiles_per_phase;
@@ -371,7 +393,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       const long long opix =
           valid ? ((long long)bb * p.out_H + yy * p.out_sy + py) * p.out_W + xx * p.out_sx + px : 0;
       const size_t obase = (size_t)opix * N;
-      const bool has_res = p.res != nullptr && (p.epi != EPI_LN_SHIFT);
+      const bool has_res = p.res != nullptr && (EPI != EPI_LN_SHIFT) && (EPI != EPI_RAW);
 
       // residual prefetch (hi / lo halves of 32 channels) — issued ahead of the TMEM waits that would expose it
       uint4 rh[4], rl[4];
@@ -408,7 +430,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       prefetch_res(0);
 
       float2 st = make_float2(0.f, 1.f);
-      if (p.epi == EPI_AFFINE) {
+      if (EPI == EPI_AFFINE) {
         if (valid) st = p.stats_in[opix];
         const int img = tb * p.TB;  // TB == 1 for per-image (attention) weights: one image per tile
         if (img != cached_img) {    // uniform across the 4 epilogue warps
@@ -427,13 +449,25 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * N);
       uint32_t v[32];
 
-      if (p.epi == EPI_BIAS || p.epi == EPI_AFFINE) {
+      if (EPI == EPI_RAW) {
+        const int su = u - t * units_per_tile;
+        const int slice = su / p.k_splits, ksp = su - slice * p.k_splits;
+        float* dst = p.raw + (size_t)ksp * p.raw_split_stride + (size_t)opix * p.Ntot + slice * N;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          tc::tmem_ld32(taddr + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<uint4*>(dst + c0)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+      } else if (EPI == EPI_BIAS || EPI == EPI_AFFINE) {
         for (int c0 = 0; c0 < N; c0 += 32) {
           tc::tmem_ld32(taddr + c0, v);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float o[8];
-            if (p.epi == EPI_AFFINE) {
+            if (EPI == EPI_AFFINE) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int c = c0 + j * 8 + k;
@@ -468,7 +502,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         }
         const float rstd = 1.f / sqrtf(sq * inv_n + 1e-5f);
         const float* shift =
-            (p.epi == EPI_LN_SHIFT && p.shift && valid) ? p.shift + (size_t)bb * p.shift_stride : nullptr;
+            (EPI == EPI_LN_SHIFT && p.shift && valid) ? p.shift + (size_t)bb * p.shift_stride : nullptr;
         float osum = 0.f, osq = 0.f;
         for (int c0 = 0; c0 < N; c0 += 32) {
           float4 sh[8];
@@ -520,6 +554,117 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   if (warp == 1) {
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second half of the sliced mode: one warp per output pixel sums the K-split partials (fixed order) and applies
+// the same fused epilogues as the in-kernel path (bias | LayerNorm+ReLU+shift | LayerNorm+ReLU+residual).
+// ------------------------------------------------------------------------------------------------
+struct LnRowsParams {
+  const float* raw;
+  int k_splits;
+  long long split_stride;
+  int N;
+  long long rows;            // output pixels
+  int pix_per_image;
+  int epi;                   // EPI_BIAS | EPI_LN_SHIFT | EPI_LN_RES
+  const float* bias;
+  const float* ln_g;
+  const float* ln_b;
+  const float* shift;
+  int shift_stride;
+  const __half* res;
+  int res_C0;
+  const __half* res2;
+  const __half* res_lo;
+  const __half* res2_lo;
+  __half* out;
+  __half* out_lo;
+  float2* stats_out;
+  int Ntot;                  // == N (name expected by load_res2)
+};
+
+__global__ void __launch_bounds__(256) ln_rows_kernel(const LnRowsParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= p.rows) return;
+  const int N = p.N, iters = N >> 6;
+  float2 v[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (i * 32 + lane) * 2;
+    v[i] = (i < iters && p.bias) ? make_float2(p.bias[c], p.bias[c + 1]) : make_float2(0.f, 0.f);
+  }
+  for (int k = 0; k < p.k_splits; ++k) {   // fixed summation order: deterministic
+    const float* src = p.raw + (size_t)k * p.split_stride + (size_t)pix * N;
+    float2 r[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < iters) r[i] = *reinterpret_cast<const float2*>(src + (i * 32 + lane) * 2);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < iters) {
+        v[i].x += r[i].x;
+        v[i].y += r[i].y;
+      }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i < iters) sum += v[i].x + v[i].y;
+  float mean = 0.f, rstd = 1.f;
+  if (p.epi != EPI_BIAS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean = sum / (float)N;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < iters) {
+        const float d0 = v[i].x - mean, d1 = v[i].y - mean;
+        sq += d0 * d0 + d1 * d1;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    rstd = 1.f / sqrtf(sq / (float)N + 1e-5f);
+  }
+  const float* shift =
+      (p.epi == EPI_LN_SHIFT && p.shift) ? p.shift + (size_t)(pix / p.pix_per_image) * p.shift_stride : nullptr;
+  float osum = 0.f, osq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i < iters) {
+      const int c = (i * 32 + lane) * 2;
+      float y0 = v[i].x, y1 = v[i].y;
+      if (p.epi != EPI_BIAS) {
+        y0 = fmaxf((y0 - mean) * rstd * p.ln_g[c] + p.ln_b[c], 0.f);
+        y1 = fmaxf((y1 - mean) * rstd * p.ln_g[c + 1] + p.ln_b[c + 1], 0.f);
+      }
+      if (shift) {
+        y0 += shift[c];
+        y1 += shift[c + 1];
+      }
+      if (p.res && p.epi != EPI_LN_SHIFT) {
+        const float2 rr = load_res2(p, pix, c);
+        y0 += rr.x;
+        y1 += rr.y;
+      }
+      const float2 q = unpack_half2(store_out2(p, (size_t)pix * N + c, y0, y1));
+      osum += q.x + q.y;
+      osq += q.x * q.x + q.y * q.y;
+    }
+  if (p.stats_out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      osum += __shfl_xor_sync(0xffffffffu, osum, o);
+      osq += __shfl_xor_sync(0xffffffffu, osq, o);
+    }
+    if (lane == 0) {
+      const float m = osum / (float)N;
+      const float var = fmaxf(osq / (float)N - m * m, 0.f);
+      p.stats_out[pix] = make_float2(m, 1.f / sqrtf(var + 1e-5f));
+    }
   }
 }
 
