@@ -797,16 +797,13 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   // tile space = output pixels (for the transposed-conv phases: the input-resolution pixels of one phase)
   const int B = pl->B, h = c.Ho, w = c.Wo, N = c.Ntot;
   TcConvParams t{};
+  // Tile = TB x TH x TW pixels, powers of two that never exceed the tensor extents; small images / batches give
+  // tiles with fewer than 128 rows (the unused accumulator rows are masked).  Every choice below is independent
+  // of what other images are in the batch, so results are bit-identical for any batch composition.
   t.TW = std::min(16, pow2floor(w));
-  if (c.groups > 1) {  // per-image weights: a tile must stay inside one image
-    t.TB = 1;
-    t.TH = 128 / t.TW;
-    if (pow2floor(h) < t.TH) return 0;
-  } else {
-    t.TH = std::min(128 / t.TW, pow2floor(h));
-    t.TB = 128 / (t.TW * t.TH);
-    if (t.TB > B) return 0;
-  }
+  t.TH = std::min(128 / t.TW, pow2floor(h));
+  t.TB = c.groups > 1 ? 1 : std::min(128 / (t.TW * t.TH), pow2floor(B));
+  t.a_bytes = 128 * t.TW * t.TH * t.TB;
   t.tiles_x = (w + t.TW - 1) / t.TW;
   t.tiles_y = (h + t.TH - 1) / t.TH;
   t.tiles_b = (B + t.TB - 1) / t.TB;
@@ -824,13 +821,16 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   // Sliced mode for layers that cannot fill the GPU with 128-pixel tiles: 64-column slices x K splits, fp32
   // partial tiles finished by ln_rows_kernel (see TcConvParams).
   const int tiles_total = t.tiles_x * t.tiles_y * t.tiles_b * (c.phases ? 4 : 1);
+  // The slicing heuristic looks at a NOMINAL batch of 8 images, not the actual one: the K-split (hence the fp32
+  // summation order) must not depend on the batch size.
+  const int tiles_nominal = ((h * w * 8 + 127) / 128) * (c.phases ? 4 : 1);
   t.Nc = N; t.n_slices = 1; t.k_splits = 1;
-  const bool sliceable = e->sliced && c.groups == 1 && op.epi != EPI_AFFINE && tiles_total < kSlicedMaxTiles && N >= 128;
+  const bool sliceable = e->sliced && c.groups == 1 && op.epi != EPI_AFFINE && tiles_nominal < kSlicedMaxTiles && N >= 128;
   if (sliceable) {
     t.Nc = 64;
     t.n_slices = N / 64;
-    const int slots = 2 * e->num_sms;
-    t.k_splits = std::max(1, std::min(c.total_chunks / 2, (slots + tiles_total * t.n_slices - 1) / (tiles_total * t.n_slices)));
+    const int slots = 2 * 148;
+    t.k_splits = std::max(1, std::min(c.total_chunks / 2, (slots + tiles_nominal * t.n_slices - 1) / (tiles_nominal * t.n_slices)));
   }
   const int Nc = t.Nc;
   t.n_split = Nc > 256 ? 2 : 1;

@@ -31,7 +31,8 @@ struct TcSeg {
 };
 
 struct TcConvParams {
-  int TW, TH, TB;            // tile = TB x TH x TW = 128 pixels
+  int TW, TH, TB;            // tile = TB x TH x TW <= 128 pixels (rows beyond it are masked)
+  int a_bytes;               // bytes of one activation box = 128 * TW*TH*TB
   int tiles_x, tiles_y, tiles_b;
   int B, H, W;               // tile-space (output) extents; source pixel = stride * tile pixel + tap offset
   int stride;
@@ -320,7 +321,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
                 const uint32_t sA = base + stage * stage_bytes;
                 const uint32_t sB = sA + 16384;
                 const uint32_t full = bar_full + 8 * stage;
-                tc::mbar_expect_tx(full, (uint32_t)stage_bytes);
+                tc::mbar_expect_tx(full, (uint32_t)(p.a_bytes + N * 128));
                 tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp, y0 * p.stride + ky + sg.dy0 + dyp, b0);
                 for (int pc = 0; pc < p.n_split; ++pc)
                   tc::tma_load_2d(sB + pc * p.n_piece * 128, &maps.b, full, 0, wrow0 + q * p.Ntot + pc * p.n_piece);
@@ -388,7 +389,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       r -= tb * p.tiles_x * p.tiles_y;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int xx = tx * p.TW + lx, yy = ty * p.TH + ly, bb = tb * p.TB + lb;
-      const bool valid = xx < p.W && yy < p.H && bb < p.B;
+      const bool valid = xx < p.W && yy < p.H && lb < p.TB && bb < p.B;
       const int py = p.phases > 1 ? (ph >> 1) : 0, px = p.phases > 1 ? (ph & 1) : 0;
       const long long opix =
           valid ? ((long long)bb * p.out_H + yy * p.out_sy + py) * p.out_W + xx * p.out_sx + px : 0;

@@ -52,8 +52,8 @@ def test_algorithmic_flops_match_survey(planner):
 def test_workspace_scales_with_batch_and_reuses_buffers(planner):
     e = planner["eps"]
     w1, w8 = e.workspace_bytes(1, 256, 256), e.workspace_bytes(8, 256, 256)
-    assert 7.5 * w1 < w8 < 8.5 * w1
-    assert w1 < 64e6            # liveness-based reuse keeps one image-step well under L2 size
+    assert 6 * w1 < w8 < 9 * w1
+    assert w1 < 100e6           # liveness-based reuse keeps one image-step under the 126 MB L2
     assert e.launches_per_step(8, 256, 256) == e.launches_per_forward(8, 256, 256) + 1
 
 
