@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
   __half* Vs = reinterpret_cast<__half*>(smem + 2 * AttnCtxSmem::kStage + AttnCtxSmem::kKs + AttnCtxSmem::kPs);
   float* m_run = reinterpret_cast<float*>(smem + 2 * AttnCtxSmem::kStage + AttnCtxSmem::kKs + AttnCtxSmem::kPs +
                                           AttnCtxSmem::kVs);
-  float* alpha = m_run + 64;
-  float* s_run = m_run + 128;
+  float* alpha = m_run + 128;   // m_run holds two copies (ping-pong per tile)
+  float* s_run = m_run + 192;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
 
   if (tid < 64) {
     m_run[tid] = -INFINITY;
+    m_run[64 + tid] = -INFINITY;
     s_run[tid] = 0.f;
     alpha[tid] = 0.f;
   }
@@ -147,6 +148,10 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
     if (cc == cb - 1) {
       // ---- K/V epilogue for this 64-pixel tile ----
       const int tile_pix = pix_begin + t * 64;
+      const int par = t & 1;                       // m_run is ping-ponged per tile (read old / write new)
+      float cmx[4][2];                             // per-thread column max over its 4 rows (K warps)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) cmx[nt][0] = cmx[nt][1] = -INFINITY;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -169,8 +174,8 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
               }
               acc[mt][nt][2 * h] = v0;
               acc[mt][nt][2 * h + 1] = v1;
-              Ks[row * 65 + col] = v0;
-              Ks[row * 65 + col + 1] = v1;
+              cmx[nt][0] = fmaxf(cmx[nt][0], v0);
+              cmx[nt][1] = fmaxf(cmx[nt][1], v1);
             } else {
               if (!valid) {
                 v0 = 0.f;
@@ -180,17 +185,36 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
             }
           }
         }
-      __syncthreads();
-      if (tid < 64) {
-        float tmax = -INFINITY;
-        for (int r = 0; r < 64; ++r) tmax = fmaxf(tmax, Ks[r * 65 + tid]);
-        const float m_old = m_run[tid];
-        const float m_new = fmaxf(m_old, tmax);
-        alpha[tid] = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
-        m_run[tid] = m_new;
+      if (wn < 2) {  // column max over the warp's 32 rows: lanes sharing (lane & 3) hold the same columns
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            float m = cmx[nt][e2];
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            if ((lane >> 2) == 0) Ks[wm * 64 + wn * 32 + nt * 8 + (lane & 3) * 2 + e2] = m;   // cmax[wm][col]
+          }
       }
       __syncthreads();
       if (wn < 2) {
+        float csum[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          csum[nt][0] = csum[nt][1] = 0.f;
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int col = wn * 32 + nt * 8 + (lane & 3) * 2 + e2;
+            const float m_old = m_run[par * 64 + col];
+            const float m_new = fmaxf(m_old, fmaxf(Ks[col], Ks[64 + col]));
+            cmx[nt][e2] = m_new;
+            if (wm == 0 && (lane >> 2) == 0) {   // one writer per column
+              m_run[(par ^ 1) * 64 + col] = m_new;
+              alpha[col] = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
+            }
+          }
+        }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -199,18 +223,28 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
               const int col = wn * 32 + nt * 8 + (lane & 3) * 2;
-              const float p0 = __expf(acc[mt][nt][2 * h] - m_run[col]);       // exp(-inf) = 0 for padded rows
-              const float p1 = __expf(acc[mt][nt][2 * h + 1] - m_run[col + 1]);
-              *reinterpret_cast<uint32_t*>(Ps + row * 72 + col) = pack_half2(p0, p1);
+              const float p0 = __expf(acc[mt][nt][2 * h] - cmx[nt][0]);       // exp(-inf) = 0 for padded rows
+              const float p1 = __expf(acc[mt][nt][2 * h + 1] - cmx[nt][1]);
+              const uint32_t hv = pack_half2(p0, p1);
+              *reinterpret_cast<uint32_t*>(Ps + row * 72 + col) = hv;
+              const float2 q = unpack_half2(hv);   // sum what the MMA will actually see
+              csum[nt][0] += q.x;
+              csum[nt][1] += q.y;
             }
+          }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            float sv = csum[nt][e2];
+            sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 8);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 16);
+            if ((lane >> 2) == 0) Ks[128 + wm * 64 + wn * 32 + nt * 8 + (lane & 3) * 2 + e2] = sv;  // csum[wm][col]
           }
       }
       __syncthreads();
-      if (tid < 64) {
-        float s = 0.f;
-        for (int r = 0; r < 64; ++r) s += __half2float(Ps[r * 72 + tid]);
-        s_run[tid] = s_run[tid] * alpha[tid] + s;
-      }
+      if (tid < 64) s_run[tid] = s_run[tid] * alpha[tid] + Ks[128 + tid] + Ks[192 + tid];
       // ---- ctx[d,e] = ctx*alpha[d] + P^T V ; warps 2(d) x 4(e), warp tile 32 x 16 ----
       {
         const int wd = warp >> 2, we = warp & 3;
@@ -268,7 +302,7 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
       }
     if (eblk == 0 && tid < 64) {
       const size_t o = ((size_t)b * p.nchunks + chunk) * C + dblk * 64 + tid;
-      p.part_m[o] = m_run[tid];
+      p.part_m[o] = m_run[(ntiles & 1) * 64 + tid];
       p.part_s[o] = s_run[tid];
     }
   }
@@ -294,44 +328,82 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_ctx, const fl
   }
 }
 
-// Batched fp32 GEMM  Cout[b][m][n] = sum_k At[b][k][m] * Bm[b][k][n]  (M, N, K multiples of 64/64/16).
+// Batched fp32 GEMM  Cout[b][m][n] = sum_k At[b][k][m] * Bm[b][k][n]   (M % TM == 0, N % 64 == 0, K % 16 == 0).
+// TM x 64 output tile per CTA, (TM/16) x 4 register tile per thread, K stepped by 16 with register prefetch of the
+// next slab.  fp32 throughout: these are the per-image C x C products behind M_b = W_out ctx^T (C^-1/2 W_q).
+template <int TM>
 __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ At, const float* __restrict__ Bm,
                                                        float* __restrict__ Cout, int M, int N, int K,
                                                        long long sA, long long sB, long long sC) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
+  constexpr int RM = TM / 16;            // rows per thread
+  constexpr int AV = TM * 16 / 4 / 256;  // float4 loads of the A slab per thread
+  __shared__ __align__(16) float As[2][16][TM];
+  __shared__ __align__(16) float Bs[2][16][64];
   const int b = blockIdx.z;
   At += (size_t)b * sA;
   Bm += (size_t)b * sB;
   Cout += (size_t)b * sC;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-      const int kk = i >> 6, mm = i & 63;
-      As[kk][mm] = At[(size_t)(k0 + kk) * M + m0 + mm];
-      Bs[kk][mm] = Bm[(size_t)(k0 + kk) * N + n0 + mm];
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[RM][4];
+#pragma unroll
+  for (int i = 0; i < RM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float4 ra[AV], rb;
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int v = 0; v < AV; ++v) {
+      const int idx = tid + v * 256;                 // float4 index inside the 16 x TM slab
+      const int kk = idx / (TM / 4), mm = (idx - kk * (TM / 4)) * 4;
+      ra[v] = *reinterpret_cast<const float4*>(At + (size_t)(k0 + kk) * M + m0 + mm);
     }
-    __syncthreads();
+    const int kk = tid >> 4, nn = (tid & 15) * 4;
+    rb = *reinterpret_cast<const float4*>(Bm + (size_t)(k0 + kk) * N + n0 + nn);
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int v = 0; v < AV; ++v) {
+      const int idx = tid + v * 256;
+      const int kk = idx / (TM / 4), mm = (idx - kk * (TM / 4)) * 4;
+      *reinterpret_cast<float4*>(&As[buf][kk][mm]) = ra[v];
+    }
+    *reinterpret_cast<float4*>(&Bs[buf][tid >> 4][(tid & 15) * 4]) = rb;
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const bool more = k0 + 16 < K;
+    if (more) gload(k0 + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], bb[4];
+      float a[RM];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < RM; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&As[buf][kk][ty * RM + i]);
+        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      }
+      const float4 bb = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      for (int i = 0; i < RM; ++i) {
+        acc[i][0] = fmaf(a[i], bb.x, acc[i][0]);
+        acc[i][1] = fmaf(a[i], bb.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], bb.z, acc[i][2]);
+        acc[i][3] = fmaf(a[i], bb.w, acc[i][3]);
+      }
     }
-    __syncthreads();
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Cout[(size_t)(m0 + ty * 4 + i) * N + n0 + tx * 4 + j] = acc[i][j];
+  for (int i = 0; i < RM; ++i)
+    *reinterpret_cast<float4*>(Cout + (size_t)(m0 + ty * RM + i) * N + n0 + tx * 4) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 }
 
 // Per (image, output row o): Mg16 = half(M[o][:] * g), um = rowsum(float(Mg16)), cm = M[o][:].b_ln + b_out[o].

@@ -710,7 +710,8 @@ struct Builder {
       op.kind = OP_SGEMM;
       op.name = name + "T";
       op.sg = {ws<float>(ctxn), dptr<float>(e, w.wq), ws<float>(T), C, C, C, (long long)C * C, 0, (long long)C * C};
-      op.grid = dim3(C / 64, C / 64, B);
+      op.bm = (C % 128 == 0 && C >= 384) ? 128 : 64;   // tile rows: keep >= ~128 CTAs in flight at B=8
+      op.grid = dim3(C / 64, C / op.bm, B);
     }
     raw_free(ctxn, cc_b);
     const size_t Mf = raw_alloc(cc_b);
@@ -720,7 +721,8 @@ struct Builder {
       op.kind = OP_SGEMM;
       op.name = name + "M";
       op.sg = {dptr<float>(e, w.woT), ws<float>(T), ws<float>(Mf), C, C, C, 0, (long long)C * C, (long long)C * C};
-      op.grid = dim3(C / 64, C / 64, B);
+      op.bm = (C % 128 == 0 && C >= 384) ? 128 : 64;
+      op.grid = dim3(C / 64, C / op.bm, B);
     }
     raw_free(T, cc_b);
     const size_t mg_b = (size_t)B * C * C * 2, v_b = (size_t)B * C * 4;
@@ -1153,8 +1155,12 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
                                                      op.comb.out);
         break;
       case OP_SGEMM:
-        sgemm_tn_kernel<<<op.grid, 256, 0, st>>>(op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N, op.sg.K, op.sg.sA,
-                                                 op.sg.sB, op.sg.sC);
+        if (op.bm == 128)
+          sgemm_tn_kernel<128><<<op.grid, 256, 0, st>>>(op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N, op.sg.K,
+                                                        op.sg.sA, op.sg.sB, op.sg.sC);
+        else
+          sgemm_tn_kernel<64><<<op.grid, 256, 0, st>>>(op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N, op.sg.K,
+                                                       op.sg.sA, op.sg.sB, op.sg.sC);
         break;
       case OP_LNROWS:
         ln_rows_kernel<<<op.grid, 256, 0, st>>>(op.lnr);

@@ -276,7 +276,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   // epilogue vectors -> smem (all threads)
-  for (int i = threadIdx.x; i < N; i += kTcThreads) {
+  for (int i = threadIdx.x; i < (EPI == EPI_RAW ? 0 : N); i += kTcThreads) {
     s_vec[i] = p.bias ? p.bias[i] : 0.f;
     s_vec[384 + i] = p.ln_g ? p.ln_g[i] : 1.f;
     s_vec[768 + i] = p.ln_b ? p.ln_b[i] : 0.f;
