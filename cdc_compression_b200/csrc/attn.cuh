@@ -40,6 +40,8 @@ struct AttnCtxSmem {
 };
 
 __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   float* Ks = reinterpret_cast<float*>(smem + 2 * AttnCtxSmem::kStage);
@@ -312,6 +314,8 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
 __global__ void attn_combine_kernel(const float* __restrict__ part_ctx, const float* __restrict__ part_m,
                                     const float* __restrict__ part_s, int C, int nchunks,
                                     float* __restrict__ ctxn) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int d = blockIdx.x, b = blockIdx.y;
   const float* pm = part_m + (size_t)b * nchunks * C + d;
   const float* ps = part_s + (size_t)b * nchunks * C + d;
@@ -339,6 +343,8 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
   constexpr int AV = TM * 16 / 4 / 256;  // float4 loads of the A slab per thread
   __shared__ __align__(16) float As[2][16][TM];
   __shared__ __align__(16) float Bs[2][16][64];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z;
   At += (size_t)b * sA;
   Bm += (size_t)b * sB;
@@ -411,6 +417,8 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
 __global__ void attn_finish_kernel(const float* __restrict__ Mf, const float* __restrict__ g,
                                    const float* __restrict__ bln, const float* __restrict__ bout, int C,
                                    __half* __restrict__ Mg16, float* __restrict__ um, float* __restrict__ cm) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int o = blockIdx.x, b = blockIdx.y;
   const float* row = Mf + ((size_t)b * C + o) * C;
   __half* dst = Mg16 + (size_t)b * C * C;

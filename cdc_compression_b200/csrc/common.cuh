@@ -55,4 +55,9 @@ __device__ __forceinline__ uint32_t swz128(int row, int chunk) {
   return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// Programmatic dependent launch (no-ops when the launch does not carry the attribute): let the next kernel's CTAs
+// be scheduled while this grid still runs, and block until every prerequisite grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace cdc

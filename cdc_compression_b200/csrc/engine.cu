@@ -197,6 +197,7 @@ struct cdc_engine {
   int mainloop = 1;   // 0 = mma.sync kernels, 1 = tcgen05/TMA kernels for stride-1 convolutions (default)
   int num_sms = 148;
   bool sliced = true;  // CDC_SLICED=0 disables the sliced low-resolution mode (A/B measurements)
+  int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
   // derived structure
   std::vector<int> dims, cdims;
   bool fold_ctx0 = false;  // small level-0 context folded into the packed input (eps demo)
@@ -466,6 +467,23 @@ int pack_attn(cdc_engine* e, const std::string& p, int C, AttnW* out) {
 }
 
 // ---------------------------------------------------------------- kernel dispatch
+bool g_pdl = false;  // programmatic dependent launch (CDC_PDL=1 enables): measured 2.6 % SLOWER inside the step graph
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int BM, int BN, int EPI>
 cudaError_t launch_igemm_t(const Op& op, cudaStream_t st) {
   static bool attr_set[16] = {};
@@ -477,8 +495,7 @@ cudaError_t launch_igemm_t(const Op& op, cudaStream_t st) {
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
-  igemm_hmma_kernel<BM, BN, EPI><<<op.grid, 256, IgemmSmem<BM, BN>::kBytes, st>>>(op.conv);
-  return cudaGetLastError();
+  return launch_k(igemm_hmma_kernel<BM, BN, EPI>, op.grid, dim3(256), IgemmSmem<BM, BN>::kBytes, st, op.conv);
 }
 
 cudaError_t launch_igemm(const Op& op, cudaStream_t st) {
@@ -504,8 +521,7 @@ cudaError_t launch_tc_t(const Op& op, cudaStream_t st) {
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
-  igemm_tc_kernel<EPI, OCC><<<op.tc_grid, kTcThreads, op.tc_smem, st>>>(op.maps, op.tcp);
-  return cudaGetLastError();
+  return launch_k(igemm_tc_kernel<EPI, OCC>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st, op.maps, op.tcp);
 }
 
 cudaError_t launch_tc(const Op& op, cudaStream_t st) {
@@ -831,8 +847,9 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   if (sliceable) {
     t.Nc = 64;
     t.n_slices = N / 64;
-    const int slots = 2 * 148;
-    t.k_splits = std::max(1, std::min(c.total_chunks / 2, (slots + tiles_nominal * t.n_slices - 1) / (tiles_nominal * t.n_slices)));
+    const int slots = e->slice_slots;
+    t.k_splits = std::max(1, std::min(std::min(c.total_chunks / 2, e->slice_kmax),
+                                      (slots + tiles_nominal * t.n_slices - 1) / (tiles_nominal * t.n_slices)));
   }
   const int Nc = t.Nc;
   t.n_split = Nc > 256 ? 2 : 1;
@@ -1119,19 +1136,20 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
     switch (op.kind) {
       case OP_TIME: {
         const size_t sm = (size_t)5 * cfg.dim * 4;
-        time_mlp_kernel<<<dim3(B, (e->R + 255) / 256), 256, sm, st>>>(a.time, a.time ? nullptr : e->d_table, e->d_step,
-                                            dptr<float>(e, e->t_w1), dptr<float>(e, e->t_b1), dptr<float>(e, e->t_w2),
-                                            dptr<float>(e, e->t_b2), dptr<float>(e, e->t_wcat),
-                                            dptr<float>(e, e->t_bcat), cfg.dim, e->R,
-                                            reinterpret_cast<float*>(pl->ws + pl->shifts_off));
+        launch_k(time_mlp_kernel, dim3(B, (e->R + 255) / 256), dim3(256), sm, st, a.time,
+                 a.time ? (const cdc_step_coef*)nullptr : (const cdc_step_coef*)e->d_table, (const int*)e->d_step,
+                 (const float*)dptr<float>(e, e->t_w1), (const float*)dptr<float>(e, e->t_b1),
+                 (const float*)dptr<float>(e, e->t_w2), (const float*)dptr<float>(e, e->t_b2),
+                 (const float*)dptr<float>(e, e->t_wcat), (const float*)dptr<float>(e, e->t_bcat), cfg.dim, e->R,
+                 reinterpret_cast<float*>(pl->ws + pl->shifts_off));
         break;
       }
       case OP_PACK: {
         const long long total = (long long)B * H * W * 8;
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
         const float* c0 = e->fold_ctx0 ? reinterpret_cast<const float*>(pl->ws + pl->ctx_off[0]) : nullptr;
-        pack_input_kernel<<<blocks, 256, 0, st>>>(a.x, cfg.channels, c0, e->fold_ctx0 ? cfg.context_channels : 0, B, H,
-                                                  W, const_cast<__half*>(op.dbg));
+        launch_k(pack_input_kernel, dim3(blocks), dim3(256), 0, st, a.x, (int)cfg.channels, c0,
+                 (int)(e->fold_ctx0 ? cfg.context_channels : 0), B, H, W, const_cast<__half*>(op.dbg));
         break;
       }
       case OP_CONV: {
@@ -1148,26 +1166,26 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         break;
       }
       case OP_ATTN_CTX:
-        attn_ctx_kernel<<<op.grid, 256, AttnCtxSmem::kBytes, st>>>(op.actx);
+        launch_k(attn_ctx_kernel, op.grid, dim3(256), (size_t)AttnCtxSmem::kBytes, st, op.actx);
         break;
       case OP_COMBINE:
-        attn_combine_kernel<<<op.grid, 128, 0, st>>>(op.comb.pc, op.comb.pm, op.comb.ps, op.comb.C, op.comb.nchunks,
-                                                     op.comb.out);
+        launch_k(attn_combine_kernel, op.grid, dim3(128), 0, st, op.comb.pc, op.comb.pm, op.comb.ps, op.comb.C,
+                 op.comb.nchunks, op.comb.out);
         break;
       case OP_SGEMM:
         if (op.bm == 128)
-          sgemm_tn_kernel<128><<<op.grid, 256, 0, st>>>(op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N, op.sg.K,
-                                                        op.sg.sA, op.sg.sB, op.sg.sC);
+          launch_k(sgemm_tn_kernel<128>, op.grid, dim3(256), 0, st, op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N,
+                   op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC);
         else
-          sgemm_tn_kernel<64><<<op.grid, 256, 0, st>>>(op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N, op.sg.K,
-                                                       op.sg.sA, op.sg.sB, op.sg.sC);
+          launch_k(sgemm_tn_kernel<64>, op.grid, dim3(256), 0, st, op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N,
+                   op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC);
         break;
       case OP_LNROWS:
-        ln_rows_kernel<<<op.grid, 256, 0, st>>>(op.lnr);
+        launch_k(ln_rows_kernel, op.grid, dim3(256), 0, st, op.lnr);
         break;
       case OP_FINISH:
-        attn_finish_kernel<<<op.grid, 128, 0, st>>>(op.fin.Mf, op.fin.g, op.fin.bln, op.fin.bout, op.fin.C, op.fin.Mg,
-                                                    op.fin.um, op.fin.cm);
+        launch_k(attn_finish_kernel, op.grid, dim3(128), 0, st, op.fin.Mf, op.fin.g, op.fin.bln, op.fin.bout, op.fin.C,
+                 op.fin.Mg, op.fin.um, op.fin.cm);
         break;
       case OP_FINAL: {
         FinalParams fp{};
@@ -1187,7 +1205,7 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         fp.variant = cfg.variant;
         fp.pred_mode = a.pred;
         fp.clip_mode = a.clip;
-        final_conv_kernel<<<dim3(W / 16, H / 16, B), 256, kFinalSmemBytes, st>>>(fp);
+        launch_k(final_conv_kernel, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes, st, fp);
         break;
       }
       default:
@@ -1206,7 +1224,7 @@ int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
     if (rc) return rc;
   }
   if (a.advance) {
-    advance_step_kernel<<<1, 32, 0, st>>>(e->d_step);
+    launch_k(advance_step_kernel, dim3(1), dim3(32), 0, st, e->d_step);
   }
   e->last_plan = pl;
   e->last_args = a;
@@ -1297,6 +1315,9 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
     return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
+  if (const char* v = getenv("CDC_PDL")) g_pdl = atoi(v) != 0;
+  if (const char* v = getenv("CDC_SLICE_SLOTS")) e->slice_slots = std::max(1, atoi(v));
+  if (const char* v = getenv("CDC_SLICE_KMAX")) e->slice_kmax = std::max(1, atoi(v));
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   *out = e.release();

@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(256) igemm_hmma_kernel(const ConvParams p) {
   __shared__ float red_a[WN][BM];
   __shared__ float red_b[WN][BM];
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / WN, wn = warp % WN;
   const uint32_t smem_base = smem_u32(smem);

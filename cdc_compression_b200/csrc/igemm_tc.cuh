@@ -257,6 +257,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   int tmem_cols = 32;
   while (tmem_cols < p.nbuf * N) tmem_cols <<= 1;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nseg; ++i) tc::prefetch_tmap(&maps.a[i]);
     tc::prefetch_tmap(&maps.b);
@@ -285,6 +286,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  pdl_wait();   // everything above (barriers, TMEM, constant vectors) overlapped the previous kernel's tail
 
   const int tiles_per_phase = p.tiles_x * p.tiles_y * p.tiles_b;
   const int total_tiles = tiles_per_phase * p.phases;
@@ -587,6 +589,8 @@ struct LnRowsParams {
 };
 
 __global__ void __launch_bounds__(256) ln_rows_kernel(const LnRowsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pix >= p.rows) return;
@@ -597,18 +601,25 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnRowsParams p) {
     const int c = (i * 32 + lane) * 2;
     v[i] = (i < iters && p.bias) ? make_float2(p.bias[c], p.bias[c + 1]) : make_float2(0.f, 0.f);
   }
-  for (int k = 0; k < p.k_splits; ++k) {   // fixed summation order: deterministic
-    const float* src = p.raw + (size_t)k * p.split_stride + (size_t)pix * N;
-    float2 r[6];
+  // fixed summation order (deterministic); K partials are fetched four at a time so their latencies overlap
+  for (int k0 = 0; k0 < p.k_splits; k0 += 4) {
+    float2 r[4][6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if (i < iters) r[i] = *reinterpret_cast<const float2*>(src + (i * 32 + lane) * 2);
+    for (int kk = 0; kk < 4; ++kk) {
+      const float* src = p.raw + (size_t)(k0 + kk) * p.split_stride + (size_t)pix * N;
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if (i < iters) {
-        v[i].x += r[i].x;
-        v[i].y += r[i].y;
-      }
+      for (int i = 0; i < 6; ++i)
+        r[kk][i] = (i < iters && k0 + kk < p.k_splits) ? *reinterpret_cast<const float2*>(src + (i * 32 + lane) * 2)
+                                                       : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        if (i < iters) {
+          v[i].x += r[kk][i].x;
+          v[i].y += r[kk][i].y;
+        }
   }
   float sum = 0.f;
 #pragma unroll

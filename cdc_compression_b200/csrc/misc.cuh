@@ -13,6 +13,8 @@ namespace cdc {
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_input_kernel(const float* __restrict__ x, int cx, const float* __restrict__ ctx, int cc,
                                   int B, int H, int W, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * H * W * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -66,6 +68,8 @@ __global__ void time_mlp_kernel(const float* __restrict__ time, const cdc_step_c
                                 const float* __restrict__ b1, const float* __restrict__ W2,
                                 const float* __restrict__ b2, const float* __restrict__ Wcat,
                                 const float* __restrict__ bcat, int dim, int R, float* __restrict__ shifts) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* hid = sm;            // [4*dim]
   float* act = sm + 4 * dim;  // [dim]
@@ -97,6 +101,8 @@ __global__ void time_mlp_kernel(const float* __restrict__ time, const cdc_step_c
 }
 
 __global__ void advance_step_kernel(int* step_ptr) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) *step_ptr -= 1;
 }
 
@@ -135,12 +141,14 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z, y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
 
-  // weights -> smem (16B copies; 8*3144*2 bytes)
+  pdl_launch_dependents();
+  // weights -> smem (16B copies; 8*3144*2 bytes) — constant data, overlaps the tail of the previous kernel
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.Wf);
     uint4* dst = reinterpret_cast<uint4*>(sW);
     for (int i = tid; i < 8 * kFinalWStride * 2 / 16; i += 256) dst[i] = src[i];
   }
+  pdl_wait();
   // halo load + LayerNorm: 8 threads per pixel, 8 channels each
   {
     const int j = tid & 7;
