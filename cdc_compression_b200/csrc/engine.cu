@@ -99,7 +99,7 @@ struct Op {
   bool use_tc = false;
   TcMaps maps;
   TcConvParams tcp{};
-  int tc_grid = 0, tc_smem = 0;
+  int tc_grid = 0, tc_smem = 0, tc_occ = 1;
   LnRowsParams lnr{};   // OP_LNROWS: second half of a sliced convolution
   // debug view of the op's fp16 NHWC output (if any)
   const __half* dbg = nullptr;
@@ -196,6 +196,7 @@ struct cdc_engine {
   bool debug_no_reuse = false;
   int mainloop = 1;   // 0 = mma.sync kernels, 1 = tcgen05/TMA kernels for stride-1 convolutions (default)
   int num_sms = 148;
+  int vreuse = 1;      // CDC_VREUSE: 0 off, 1 when it fits the default occupancy, 2 also at one CTA per SM
   bool sliced = true;  // CDC_SLICED=0 disables the sliced low-resolution mode (A/B measurements)
   int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
   // derived structure
@@ -525,7 +526,7 @@ cudaError_t launch_tc_t(const Op& op, cudaStream_t st) {
 }
 
 cudaError_t launch_tc(const Op& op, cudaStream_t st) {
-  const int occ = op.tcp.Nc <= 128 ? 2 : 1;
+  const int occ = op.tc_occ;
 #define CASE(E_)                                                \
   if (op.tcp.epi == E_) {                                       \
     return occ == 2 ? launch_tc_t<E_, 2>(op, st) : launch_tc_t<E_, 1>(op, st); \
@@ -821,18 +822,22 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.TW = std::min(16, pow2floor(w));
   t.TH = std::min(128 / t.TW, pow2floor(h));
   t.TB = c.groups > 1 ? 1 : std::min(128 / (t.TW * t.TH), pow2floor(B));
-  t.a_bytes = 128 * t.TW * t.TH * t.TB;
+  const int a_rows = t.TW * t.TH * t.TB;
   t.tiles_x = (w + t.TW - 1) / t.TW;
   t.tiles_y = (h + t.TH - 1) / t.TH;
   t.tiles_b = (B + t.TB - 1) / t.TB;
   t.B = B; t.H = h; t.W = w;
   t.stride = c.stride;
   t.nseg = c.nseg;
-  for (int i = 0; i < c.nseg; ++i) {
+  for (int i = 0, q0 = 0; i < c.nseg; ++i) {
     t.seg[i].cpt = c.seg[i].C / 64;
     t.seg[i].kh = c.seg[i].kh; t.seg[i].kw = c.seg[i].kw;
     t.seg[i].dy0 = c.seg[i].dy0; t.seg[i].dx0 = c.seg[i].dx0;
     t.seg[i].nchunk = c.seg[i].nchunk;
+    t.seg[i].vr = 1;
+    t.seg[i].a_bytes = 128 * a_rows;
+    t.seg[i].q0 = q0;
+    q0 += c.seg[i].nchunk;
   }
   t.total_chunks = c.total_chunks;
   t.Ntot = N;
@@ -856,9 +861,40 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.n_piece = Nc / t.n_split;
   t.nbuf = (2 * Nc <= 512) ? 2 : 1;
   // Nc <= 128: two CTAs per SM (2 x 256 TMEM columns, half the shared memory each) double the epilogue warps
-  const int ctas_per_sm = Nc <= 128 ? 2 : 1;
-  const int budget = (227 * 1024) / ctas_per_sm - 1024 - 5 * 384 * 4 - 256 - (ctas_per_sm > 1 ? 1024 : 0);
-  t.stages = std::max(2, std::min(kTcMaxStages, budget / tc_stage_bytes(Nc)));
+  int ctas_per_sm = Nc <= 128 ? 2 : 1;
+  auto smem_budget = [](int ctas) { return (227 * 1024) / ctas - 1024 - 5 * 384 * 4 - 256 - (ctas > 1 ? 1024 : 0); };
+  int budget = smem_budget(ctas_per_sm);
+  // Vertical reuse: one activation box of TH+kh-1 tile rows serves all kh vertical taps of a (kx, channel chunk) —
+  // tap ky reads it TW pixel rows further down, which is a whole number of 1024-byte swizzle atoms when TW is
+  // 8 or 16.  Cuts the L2->SM activation traffic of a 3x3 conv from 9 to 3.75 tile loads (the top levels are
+  // L2-bandwidth bound).  Needs one image per tile and >= 2 pipeline stages of (box + kh weight tiles).
+  t.b_off = 16384;
+  t.vr_max = 1;
+  t.total_sc = c.total_chunks;
+  const bool vr_ok = e->vreuse && !sliceable && c.stride == 1 && !c.phases && t.TB == 1 && (t.TW == 8 || t.TW == 16) &&
+                     a_rows == 128;
+  if (vr_ok) {
+    int khmax = 1;
+    for (int i = 0; i < c.nseg; ++i) khmax = std::max(khmax, c.seg[i].kh);
+    const int b_off = ((128 * t.TW * (t.TH + khmax - 1)) + 1023) & ~1023;
+    if (khmax > 1 && budget / tc_stage_bytes(b_off, khmax, Nc) < 2 && e->vreuse >= 2 && ctas_per_sm == 2 &&
+        smem_budget(1) / tc_stage_bytes(b_off, khmax, Nc) >= 2) {
+      ctas_per_sm = 1;   // trade the second CTA for the reuse pipeline (CDC_VREUSE=2)
+      budget = smem_budget(1);
+    }
+    if (khmax > 1 && budget / tc_stage_bytes(b_off, khmax, Nc) >= 2) {
+      t.b_off = b_off;
+      t.vr_max = khmax;
+      t.total_sc = 0;
+      for (int i = 0; i < c.nseg; ++i) {
+        t.seg[i].vr = c.seg[i].kh;
+        t.seg[i].a_bytes = 128 * t.TW * (t.TH + c.seg[i].kh - 1);
+        t.total_sc += c.seg[i].kw * t.seg[i].cpt;
+      }
+    }
+  }
+  const int stage_bytes = tc_stage_bytes(t.b_off, t.vr_max, Nc);
+  t.stages = std::max(2, std::min(kTcMaxStages, budget / stage_bytes));
   t.phases = c.phases ? 4 : 1;
   t.w_rows_per_phase = c.total_chunks * N;
   t.w_rows_per_image = c.groups > 1 ? c.total_chunks * N : 0;
@@ -867,7 +903,8 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.bias = c.bias; t.ln_g = c.ln_g; t.ln_b = c.ln_b; t.shift = c.shift; t.shift_stride = c.shift_stride;
   t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2; t.res_lo = c.res_lo; t.res2_lo = c.res2_lo;
   t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
-  op.tc_smem = tc_smem_bytes(Nc, t.stages);
+  op.tc_smem = tc_smem_bytes(stage_bytes, t.stages);
+  op.tc_occ = ctas_per_sm;
   op.tc_grid = std::min(tiles_total * t.n_slices * t.k_splits, e->num_sms * ctas_per_sm);
   if (sliceable) {
     const long long out_pix = (long long)B * c.out_H * c.out_W;
@@ -887,7 +924,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     cuuint64_t gstr[3] = {Cs * 2, ws_ * Cs * 2, hs_ * ws_ * Cs * 2};
     // strided convolution: the box spans stride*T source pixels, of which every stride-th is loaded
     const cuuint32_t sx = (cuuint32_t)c.stride;
-    cuuint32_t box[4] = {64, (cuuint32_t)t.TW * sx, (cuuint32_t)t.TH * sx, (cuuint32_t)t.TB};
+    cuuint32_t box[4] = {64, (cuuint32_t)t.TW * sx, (cuuint32_t)(t.TH + t.seg[i].vr - 1) * sx, (cuuint32_t)t.TB};
     cuuint32_t estr[4] = {1, sx, sx, 1};
     CUresult r = enc(&op.maps.a[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)c.seg[i].src, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1315,6 +1352,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
     return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
+  if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
   if (const char* v = getenv("CDC_PDL")) g_pdl = atoi(v) != 0;
   if (const char* v = getenv("CDC_SLICE_SLOTS")) e->slice_slots = std::max(1, atoi(v));
   if (const char* v = getenv("CDC_SLICE_KMAX")) e->slice_kmax = std::max(1, atoi(v));

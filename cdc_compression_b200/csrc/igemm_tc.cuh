@@ -28,11 +28,16 @@ struct TcSeg {
   int kh, kw;
   int dy0, dx0;
   int nchunk;
+  int vr;        // vertical reuse: 1, or kh = one activation box of TH+kh-1 tile rows feeds all kh vertical taps
+  int a_bytes;   // bytes of this segment's activation box
+  int q0;        // first weight chunk of the segment
 };
 
 struct TcConvParams {
   int TW, TH, TB;            // tile = TB x TH x TW <= 128 pixels (rows beyond it are masked)
-  int a_bytes;               // bytes of one activation box = 128 * TW*TH*TB
+  int b_off;                 // byte offset of the weight tiles inside a pipeline stage (>= largest activation box)
+  int vr_max;                // weight tiles per stage
+  int total_sc;              // pipeline stages' worth of work per tile ("super-chunks"), split by k_splits
   int tiles_x, tiles_y, tiles_b;
   int B, H, W;               // tile-space (output) extents; source pixel = stride * tile pixel + tap offset
   int stride;
@@ -229,9 +234,9 @@ constexpr int kTcThreads = 192;
 constexpr int kTcMaxStages = 8;
 
 // dynamic smem: [stages][A 16 KB | B Ntot*128 B] (1024-aligned) + epilogue vectors + barriers
-__host__ __device__ inline int tc_stage_bytes(int Ntot) { return 16384 + Ntot * 128; }
-__host__ __device__ inline int tc_smem_bytes(int Ntot, int stages) {
-  return 1024 /*alignment slack*/ + stages * tc_stage_bytes(Ntot) + 5 * 384 * 4 + 256;
+__host__ __device__ inline int tc_stage_bytes(int b_off, int vr_max, int Nc) { return b_off + vr_max * Nc * 128; }
+__host__ __device__ inline int tc_smem_bytes(int stage_bytes, int stages) {
+  return 1024 /*alignment slack*/ + stages * stage_bytes + 5 * 384 * 4 + 256;
 }
 
 // EPI: fused epilogue (compile-time, prunes the others); OCC: CTAs per SM the register budget is sized for.
@@ -242,7 +247,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int stage_bytes = tc_stage_bytes(p.Nc);
+  const int stage_bytes = tc_stage_bytes(p.b_off, p.vr_max, p.Nc);
   float* s_vec = reinterpret_cast<float*>(smem + p.stages * stage_bytes);  // bias | g | b | (u | c): 5 x 384
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + 5 * 384 * 4);
   // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2]; then the TMEM base address word
@@ -302,7 +307,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         const int t = u / units_per_tile;
         const int su = u - t * units_per_tile;
         const int slice = su / p.k_splits, ksp = su - slice * p.k_splits;
-        const int q0 = (ksp * p.total_chunks) / p.k_splits, q1 = ((ksp + 1) * p.total_chunks) / p.k_splits;
+        const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
         const int ph = t / tiles_per_phase;
         int r = t - ph * tiles_per_phase;
         const int tb = r / (p.tiles_x * p.tiles_y);
@@ -311,22 +316,28 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB;
         const int dyp = p.phases > 1 ? (ph >> 1) - 1 : 0, dxp = p.phases > 1 ? (ph & 1) - 1 : 0;
         const int wrow0 = ph * p.w_rows_per_phase + b0 * p.w_rows_per_image + slice * N;
-        int q = 0;
+        int sc = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const TcSeg sg = p.seg[s];
           const CUtensorMap* mA = &maps.a[s];
-          for (int ky = 0; ky < sg.kh; ++ky)
+          for (int kyo = 0; kyo < sg.kh; kyo += sg.vr)
             for (int kx = 0; kx < sg.kw; ++kx)
-              for (int cc = 0; cc < sg.cpt; ++cc, ++q) {
-                if (q < q0 || q >= q1) continue;
+              for (int cc = 0; cc < sg.cpt; ++cc, ++sc) {
+                if (sc < sc0 || sc >= sc1) continue;
                 tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 const uint32_t sA = base + stage * stage_bytes;
-                const uint32_t sB = sA + 16384;
+                const uint32_t sB = sA + p.b_off;
                 const uint32_t full = bar_full + 8 * stage;
-                tc::mbar_expect_tx(full, (uint32_t)(p.a_bytes + N * 128));
-                tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp, y0 * p.stride + ky + sg.dy0 + dyp, b0);
-                for (int pc = 0; pc < p.n_split; ++pc)
-                  tc::tma_load_2d(sB + pc * p.n_piece * 128, &maps.b, full, 0, wrow0 + q * p.Ntot + pc * p.n_piece);
+                tc::mbar_expect_tx(full, (uint32_t)(sg.a_bytes + sg.vr * N * 128));
+                // one activation box: TH + vr - 1 tile rows starting at the first vertical tap
+                tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp,
+                                y0 * p.stride + kyo + sg.dy0 + dyp, b0);
+                for (int v = 0; v < sg.vr; ++v) {   // the weight tiles of the vr vertical taps it feeds
+                  const int q = sg.q0 + ((kyo + v) * sg.kw + kx) * sg.cpt + cc;
+                  for (int pc = 0; pc < p.n_split; ++pc)
+                    tc::tma_load_2d(sB + (v * p.n_split + pc) * p.n_piece * 128, &maps.b, full, 0,
+                                    wrow0 + q * p.Ntot + pc * p.n_piece);
+                }
                 if (++stage == p.stages) {
                   stage = 0;
                   phase ^= 1;
@@ -344,30 +355,41 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       int it = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
         const int ksp = u % p.k_splits;
-        const int nq = ((ksp + 1) * p.total_chunks) / p.k_splits - (ksp * p.total_chunks) / p.k_splits;
+        const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
         const int buf = it % p.nbuf;
         const uint32_t use = (uint32_t)(it / p.nbuf);  // how many times this buffer was used before
         tc::mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
-        for (int q = 0; q < nq; ++q) {
-          tc::mbar_wait(bar_full + 8 * stage, phase);
-          tc::tc_fence_after();
-          const uint32_t sA = base + stage * stage_bytes;
-          const uint32_t sB = sA + 16384;
-          const uint64_t dA = tc::make_desc_sw128(sA);
+        uint32_t accumulate = 0;
+        int sc = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int vr = p.seg[s].vr;
+          const int nsc = (p.seg[s].kh / vr) * p.seg[s].kw * p.seg[s].cpt;
+          for (int i = 0; i < nsc; ++i, ++sc) {
+            if (sc < sc0 || sc >= sc1) continue;
+            tc::mbar_wait(bar_full + 8 * stage, phase);
+            tc::tc_fence_after();
+            const uint32_t sA = base + stage * stage_bytes;
+            const uint32_t sB = sA + p.b_off;
+            for (int v = 0; v < vr; ++v) {
+              // vertical tap v reads the same box TW pixel rows (= TW*128 bytes, a multiple of the swizzle atom) down
+              const uint64_t dA = tc::make_desc_sw128(sA + v * p.TW * 128);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            for (int pc = 0; pc < p.n_split; ++pc) {
-              const uint64_t dB = tc::make_desc_sw128(sB + pc * p.n_piece * 128);
-              tc::umma_f16(d_tmem + pc * p.n_piece, dA + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), idesc,
-                           (q | ks) ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks) {
+                for (int pc = 0; pc < p.n_split; ++pc) {
+                  const uint64_t dB = tc::make_desc_sw128(sB + (v * p.n_split + pc) * p.n_piece * 128);
+                  tc::umma_f16(d_tmem + pc * p.n_piece, dA + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), idesc,
+                               accumulate);
+                }
+                accumulate = 1;
+              }
             }
-          }
-          tc::umma_commit(bar_empty + 8 * stage);  // frees this smem stage once the MMAs above retire
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+            tc::umma_commit(bar_empty + 8 * stage);  // frees this smem stage once the MMAs above retire
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
         tc::umma_commit(bar_tfull + 8 * buf);  // accumulator of this tile complete

@@ -142,14 +142,16 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
   const int b = blockIdx.z, y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
 
   pdl_launch_dependents();
-  // weights -> smem (16B copies; 8*3144*2 bytes) — constant data, overlaps the tail of the previous kernel
+  // weights -> smem with cp.async (constant data; lands while the halo is being normalised)
   {
-    const uint4* src = reinterpret_cast<const uint4*>(p.Wf);
-    uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (int i = tid; i < 8 * kFinalWStride * 2 / 16; i += 256) dst[i] = src[i];
+    const uint32_t dst = smem_u32(sW);
+    for (int i = tid; i < 8 * kFinalWStride * 2 / 16; i += 256)
+      cp_async16(dst + i * 16, reinterpret_cast<const uint4*>(p.Wf) + i, 16);
+    cp_async_commit();
   }
   pdl_wait();
-  // halo load + LayerNorm: 8 threads per pixel, 8 channels each
+  // halo load + LayerNorm: 8 threads per pixel, 8 channels each; 8 pixels per thread are fetched up front so the
+  // global-load latency is paid twice per CTA instead of once per pixel batch
   {
     const int j = tid & 7;
     float g[8], bb[8];
@@ -158,62 +160,71 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
       g[c] = p.ln_g[j * 8 + c];
       bb[c] = p.ln_b[j * 8 + c];
     }
-    for (int hp0 = 0; hp0 < kFinalHalo * kFinalHalo; hp0 += 32) {
-      const int hp = hp0 + (tid >> 3);
-      const int hy = hp / kFinalHalo, hx = hp - hy * kFinalHalo;
-      const int yy = y0 + hy - 3, xx = x0 + hx - 3;
-      const bool inb = hp < kFinalHalo * kFinalHalo && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-      float v[8];
+    constexpr int kBatch = 8;
+    for (int hp00 = 0; hp00 < kFinalHalo * kFinalHalo; hp00 += 32 * kBatch) {
+      uint4 raw[kBatch], rlo[kBatch];
+      bool inb[kBatch];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = 0.f;
-      if (inb) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(p.in + (((size_t)b * p.H + yy) * p.W + xx) * 64 + j * 8);
+      for (int u = 0; u < kBatch; ++u) {
+        const int hp = hp00 + u * 32 + (tid >> 3);
+        const int hy = hp / kFinalHalo, hx = hp - hy * kFinalHalo;
+        const int yy = y0 + hy - 3, xx = x0 + hx - 3;
+        inb[u] = hp < kFinalHalo * kFinalHalo && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        rlo[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (inb[u]) {
+          const size_t off = (((size_t)b * p.H + yy) * p.W + xx) * 64 + j * 8;
+          raw[u] = *reinterpret_cast<const uint4*>(p.in + off);
+          if (p.in_lo) rlo[u] = *reinterpret_cast<const uint4*>(p.in_lo + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int hp = hp00 + u * 32 + (tid >> 3);
+        float v[8];
         float2 f;
-        f = unpack_half2(raw.x); v[0] = f.x; v[1] = f.y;
-        f = unpack_half2(raw.y); v[2] = f.x; v[3] = f.y;
-        f = unpack_half2(raw.z); v[4] = f.x; v[5] = f.y;
-        f = unpack_half2(raw.w); v[6] = f.x; v[7] = f.y;
-        if (p.in_lo) {
-          const uint4 lo =
-              *reinterpret_cast<const uint4*>(p.in_lo + (((size_t)b * p.H + yy) * p.W + xx) * 64 + j * 8);
-          f = unpack_half2(lo.x); v[0] += f.x; v[1] += f.y;
-          f = unpack_half2(lo.y); v[2] += f.x; v[3] += f.y;
-          f = unpack_half2(lo.z); v[4] += f.x; v[5] += f.y;
-          f = unpack_half2(lo.w); v[6] += f.x; v[7] += f.y;
+        f = unpack_half2(raw[u].x); v[0] = f.x; v[1] = f.y;
+        f = unpack_half2(raw[u].y); v[2] = f.x; v[3] = f.y;
+        f = unpack_half2(raw[u].z); v[4] = f.x; v[5] = f.y;
+        f = unpack_half2(raw[u].w); v[6] = f.x; v[7] = f.y;
+        f = unpack_half2(rlo[u].x); v[0] += f.x; v[1] += f.y;
+        f = unpack_half2(rlo[u].y); v[2] += f.x; v[3] += f.y;
+        f = unpack_half2(rlo[u].z); v[4] += f.x; v[5] += f.y;
+        f = unpack_half2(rlo[u].w); v[6] += f.x; v[7] += f.y;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s += v[c];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const float mean = s * (1.f / 64.f);
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float d = v[c] - mean;
+          q += d * d;
         }
-      }
-      float s = 0.f;
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 4);
+        const float rstd = 1.f / sqrtf(q * (1.f / 64.f) + 1e-5f);
+        if (hp < kFinalHalo * kFinalHalo) {
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (inb[u]) {
+            float y[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) s += v[c];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      const float mean = s * (1.f / 64.f);
-      float q = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float d = v[c] - mean;
-        q += d * d;
-      }
-      q += __shfl_xor_sync(0xffffffffu, q, 1);
-      q += __shfl_xor_sync(0xffffffffu, q, 2);
-      q += __shfl_xor_sync(0xffffffffu, q, 4);
-      const float rstd = 1.f / sqrtf(q * (1.f / 64.f) + 1e-5f);
-      if (hp < kFinalHalo * kFinalHalo) {
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (inb) {
-          float y[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) y[c] = (v[c] - mean) * rstd * g[c] + bb[c];
-          o.x = pack_half2(y[0], y[1]);
-          o.y = pack_half2(y[2], y[3]);
-          o.z = pack_half2(y[4], y[5]);
-          o.w = pack_half2(y[6], y[7]);
+            for (int c = 0; c < 8; ++c) y[c] = (v[c] - mean) * rstd * g[c] + bb[c];
+            o.x = pack_half2(y[0], y[1]);
+            o.y = pack_half2(y[2], y[3]);
+            o.z = pack_half2(y[4], y[5]);
+            o.w = pack_half2(y[6], y[7]);
+          }
+          *reinterpret_cast<uint4*>(sIn + swz128(hp, j)) = o;
         }
-        *reinterpret_cast<uint4*>(sIn + swz128(hp, j)) = o;
       }
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
 
   float acc[2][4];
