@@ -393,3 +393,45 @@ def seeded_context(variant: str, batch: int, h: int, w: int, seed: int = 0, dim:
         gen = torch.Generator().manual_seed(77_000 + 31 * seed + l)
         out.append(torch.randn(batch, c, h >> l, w >> l, generator=gen) * 0.5)
     return out
+
+
+def seeded_fill(state_dict: StateDict, seed: int = 0, denoiser_gain: float = 1.0) -> StateDict:
+    """Deterministic replacement for a whole GaussianDiffusion state_dict (denoise_fn.* AND context_fn.*), usable on
+    the reference and on the drop-in alike (same keys).  Entropy-model constants (prior.affine.*.weight, prior.a.*,
+    prior._medians) and the train_* schedule buffers keep their constructor values."""
+    out: StateDict = {}
+    for n, (k, v) in enumerate(sorted(state_dict.items())):
+        keep = (k.startswith("train_") or ".prior.a." in k or k.endswith("prior._medians")
+                or (".prior.affine." in k and k.endswith(".weight")) or not v.is_floating_point())
+        if keep:
+            out[k] = v.clone()
+            continue
+        gen = torch.Generator().manual_seed(7_000_003 * (seed + 1) + n)
+        u = torch.rand(v.shape, generator=gen) * 2 - 1
+        if k.endswith(".g"):
+            out[k] = 1.0 + 0.2 * u
+        elif ".prior.affine." in k and k.endswith(".bias"):
+            out[k] = 0.5 * u
+        elif k.endswith(".b") or k.endswith(".bias") or v.dim() < 2:
+            out[k] = 0.1 * u
+        else:
+            shp = tuple(v.shape)
+            if len(shp) == 4 and ("dec." in k or "ups." in k) and k.endswith("conv.weight") and shp[2] in (4, 5) \
+                    and "hyper_enc" not in k and "enc." not in k.split("dec.")[0][-4:]:
+                fan_in = shp[0] * (shp[2] * shp[3]) / 4.0        # transposed conv, stride 2
+            else:
+                fan_in = float(np.prod(shp[1:]))
+            gain = denoiser_gain if k.startswith("denoise_fn.final_conv") else 1.0
+            out[k] = u * (gain * math.sqrt(3.0 / fan_in))
+    return out
+
+
+def kodak_crops(images: Sequence[Tensor], size: int = 256, count: int = 8) -> Tensor:
+    """`count` size x size crops on a fixed grid over the given [3,H,W] images (BASELINE config 2's batch)."""
+    crops = []
+    for img in images:
+        _, h, w = img.shape
+        for y in range(0, h - size + 1, size):
+            for x in range(0, w - size + 1, size):
+                crops.append(img[:, y:y + size, x:x + size])
+    return torch.stack(crops[:count])

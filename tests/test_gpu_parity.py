@@ -225,6 +225,65 @@ def test_compress_dropin_end_to_end(variant):
     assert psnr.min() > 40.0, psnr
 
 
+def _kodak():
+    from PIL import Image
+    out = []
+    for i in (1, 2, 3):
+        a = np.asarray(Image.open(os.path.join(GOLD, "imgs", f"{i}.png")).convert("RGB"), dtype=np.float32) / 255.0
+        out.append(torch.from_numpy(a).permute(2, 0, 1) * 2 - 1)
+    return out
+
+
+def _init_noise(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * 0.8
+
+
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False          # context_fn stays PyTorch: keep its convs in true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def test_kodak_decode_x_variant_matches_reference_psnr():
+    """BASELINE config 3 (shortened to S=6): the three 512x768 Kodak fixtures through the drop-in x-variant
+    compress() vs the decode produced by the UNMODIFIED reference (tests/golden/make_golden_images.py).
+    Gate: |PSNR(ours, x) - PSNR(ref, x)| <= 0.01 dB.  LPIPS cannot be measured offline (no VGG weights)."""
+    _no_tf32()
+    gold = np.load(os.path.join(GOLD, "decode_x_kodak.npz"))
+    d = build_dropin("x")
+    d.load_state_dict(O.seeded_fill(d.state_dict(), seed=0, denoiser_gain=0.5))
+    d.to(dev())
+    for i, img in enumerate(_kodak()):
+        x = img[None]
+        xh, bpp = d.compress(x.to(dev()), sample_steps=int(gold["S"]), bpp_return_mean=True,
+                             init=_init_noise(x.shape, 100 + i).to(dev()))
+        xh = xh.cpu().clamp(-1, 1)
+        ref = torch.from_numpy(gold["out"][i]).float()[None]
+        psnr_ours = O.batch_psnr(xh / 2 + 0.5, x / 2 + 0.5)[0].item()
+        assert abs(psnr_ours - float(gold["psnr"][i])) <= 0.01, (i, psnr_ours, float(gold["psnr"][i]))
+        assert O.batch_psnr(xh / 2 + 0.5, ref / 2 + 0.5)[0].item() > 45.0
+        assert abs(float(bpp) - float(gold["bpp"][i])) < 1e-3 * float(gold["bpp"][i])
+
+
+def test_kodak_crops_decode_eps_variant_matches_reference_psnr():
+    """BASELINE config 2's batch (eight 256x256 Kodak crops) through the drop-in eps-variant compress(), S=6,
+    clip_noise="full" (random-init eps models diverge without the clamp), vs the unmodified reference's decode."""
+    _no_tf32()
+    gold = np.load(os.path.join(GOLD, "decode_eps_crops.npz"))
+    d = build_dropin("eps")
+    d.clip_noise = "full"
+    d.load_state_dict(O.seeded_fill(d.state_dict(), seed=0, denoiser_gain=0.5))
+    d.to(dev())
+    x = O.kodak_crops(_kodak(), 256, 8)
+    xh, bpp = d.compress(x.to(dev()), sample_steps=int(gold["S"]), sample_mode="ddim", bpp_return_mean=False,
+                         init=_init_noise(x.shape, 200).to(dev()))
+    xh = xh.cpu().clamp(-1, 1)
+    ref = torch.from_numpy(gold["out"]).float()
+    psnr_ours = O.batch_psnr(xh / 2 + 0.5, x / 2 + 0.5)
+    assert (psnr_ours - torch.from_numpy(gold["psnr"]).float()).abs().max().item() <= 0.01
+    assert O.batch_psnr(xh / 2 + 0.5, ref / 2 + 0.5).min().item() > 40.0
+    assert torch.allclose(bpp.cpu(), torch.from_numpy(gold["bpp"]).float(), rtol=1e-3)
+
+
 def test_rng_stream_advances_like_reference():
     """The reference draws randn_like once per step even at eta=0; the drop-in leaves the CUDA generator in
     the same state so the next image's init noise is identical."""
