@@ -1149,6 +1149,10 @@ Plan* get_plan(cdc_engine* e, int B, int H, int W, void* ws, int* rc) {
     return nullptr;
   }
   if ((H >> (e->cfg.n_levels - 1)) < 1) { *rc = fail(e, CDC_ERR_INVALID, "image too small"); return nullptr; }
+  if ((long long)B * H * W * 64 >= (1ll << 31)) {
+    *rc = fail(e, CDC_ERR_INVALID, "B*H*W too large for one engine call (%d x %d x %d): split the batch", B, H, W);
+    return nullptr;
+  }
   auto key = std::make_tuple(B, H, W, (uintptr_t)ws);
   auto it = e->plans.find(key);
   if (it != e->plans.end()) return it->second.get();
@@ -1183,7 +1187,7 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
       }
       case OP_PACK: {
         const long long total = (long long)B * H * W * 8;
-        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 64);
         const float* c0 = e->fold_ctx0 ? reinterpret_cast<const float*>(pl->ws + pl->ctx_off[0]) : nullptr;
         launch_k(pack_input_kernel, dim3(blocks), dim3(256), 0, st, a.x, (int)cfg.channels, c0,
                  (int)(e->fold_ctx0 ? cfg.context_channels : 0), B, H, W, const_cast<__half*>(op.dbg));

@@ -15,29 +15,33 @@ __global__ void pack_input_kernel(const float* __restrict__ x, int cx, const flo
                                   int B, int H, int W, __half* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = (long long)B * H * W * 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int kx = (int)(i & 7);
-    const long long pix = i >> 3;
-    const int xx = (int)(pix % W);
-    const long long t = pix / W;
-    const int yy = (int)(t % H);
-    const int b = (int)(t / H);
+  const int total = B * H * W * 8;   // < 2^31 for every supported shape (checked by the engine)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kx = i & 7;
+    const int pix = i >> 3;
+    const int xx = pix % W;
+    const int t = pix / W;
+    const int yy = t % H;
+    const int b = t / H;
     const int sx = xx + kx - 3;
     float v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = 0.f;
     if (kx < 7 && sx >= 0 && sx < W) {
-      for (int c = 0; c < cx; ++c) v[c] = x[(((size_t)b * cx + c) * H + yy) * W + sx];
-      for (int c = 0; c < cc; ++c) v[cx + c] = ctx[(((size_t)b * cc + c) * H + yy) * W + sx];
+      const size_t row = (size_t)yy * W + sx;
+      const size_t plane = (size_t)H * W;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < cx) v[c] = x[((size_t)b * cx + c) * plane + row];
+        else if (c < cx + cc) v[c] = ctx[((size_t)b * cc + (c - cx)) * plane + row];
+      }
     }
     uint4 o;
     o.x = pack_half2(v[0], v[1]);
     o.y = pack_half2(v[2], v[3]);
     o.z = pack_half2(v[4], v[5]);
     o.w = pack_half2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + i * 8) = o;
+    *reinterpret_cast<uint4*>(out + (size_t)i * 8) = o;
   }
 }
 
