@@ -274,7 +274,7 @@ def run_ours(args):
     fam = {}
     for name, pms, fl in prof:
         base = name.replace("#partials", "")
-        key = ("attention" if (".2." in base or "mid_attn" in base) else
+        key = ("attention" if base.rsplit(".", 1)[-1] in ("ctx", "combine", "T", "M", "finish", "out") else
                "resample" if (base.endswith(".down") or base.endswith(".up")) else
                "res_conv" if base.endswith("res_conv") else
                "block_conv" if ("block1" in base or "block2" in base) else base)

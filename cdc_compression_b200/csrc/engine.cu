@@ -871,8 +871,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.b_off = 16384;
   t.vr_max = 1;
   t.total_sc = c.total_chunks;
-  const bool vr_ok = e->vreuse && !sliceable && c.stride == 1 && !c.phases && t.TB == 1 && (t.TW == 8 || t.TW == 16) &&
-                     a_rows == 128;
+  const bool vr_ok = e->vreuse && !sliceable && c.stride == 1 && t.TB == 1 && (t.TW == 8 || t.TW == 16) && a_rows == 128;
   if (vr_ok) {
     int khmax = 1;
     for (int i = 0; i < c.nseg; ++i) khmax = std::max(khmax, c.seg[i].kh);
