@@ -155,11 +155,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config():
+def workload_config(workspace_mb=None):
+    ws = f"{workspace_mb:.0f} MB workspace" if workspace_mb else "the engine workspace (~460 MB)"
     return {"workload": f"epsilonparam DDIM decode, {SCHEDULE}-entry schedule, batch={BATCH} {HEIGHT}x{WIDTH} per GPU "
                         "(BASELINE.json configs[1]), eta=0, clip_noise=none, seeded random-init weights",
             "variant": VARIANT, "batch_per_gpu": BATCH, "height": HEIGHT, "width": WIDTH, "schedule_steps": SCHEDULE,
-            "l2_policy": "working set per step (303 MB workspace + 80 MB weights) exceeds the 126 MB L2; no flush"}
+            "l2_policy": f"working set per step ({ws} + ~100 MB fp16 weights) exceeds the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -304,7 +305,8 @@ def run_ours(args):
     line = {
         "metric": "denoising_image_steps_per_s", "value": value, "unit": "image-steps/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(),
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": workload_config(eng.workspace_bytes(BATCH, HEIGHT, WIDTH) / 1e6),
         "mpix_per_s": value * PIX / 1e6, "batch_steps_per_s": K / (ms_max / 1e3),
         "roofline": roofline,
         "step_roofline": {"bound": "tensor", "achieved": step_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
@@ -318,11 +320,12 @@ def run_ours(args):
         "gpu_launches": launches_step * K * world, "clocks": clocks, "finite": finite,
     }
     if not args.no_cpu_baseline and world == 1:
-        n_cpu = 2
-        dt = cpu_steps(n_cpu, 2, 256, warm=1)
-        line["cpu_baseline"] = {"value": 2 * n_cpu / dt, "unit": "image-steps/s", "cores": torch.get_num_threads(),
+        n_cpu = 3
+        dt = cpu_steps(n_cpu, BATCH, 256, warm=1)
+        line["cpu_baseline"] = {"value": BATCH * n_cpu / dt, "unit": "image-steps/s", "cores": torch.get_num_threads(),
                                 "kind": "port",
-                                "sample": f"{n_cpu} DDIM steps of a 2x3x256x256 batch with the oracle port (fp32)"}
+                                "sample": f"{n_cpu} DDIM steps (+1 warm-up) of the same {BATCH}x3x256x256 batch with the "
+                                          f"oracle port, fp32, {torch.get_num_threads()} threads, {dt:.1f} s"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

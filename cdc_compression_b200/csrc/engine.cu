@@ -100,6 +100,10 @@ struct Op {
   TcMaps maps;
   TcConvParams tcp{};
   int tc_grid = 0, tc_smem = 0, tc_occ = 1;
+  // stream lane: 1 = runs on the engine's side stream concurrently with the main-lane ops that follow it (the 1x1
+  // res_conv of a ResnetBlock overlaps block1); join_before = main lane must wait for the side lane first
+  int lane = 0;
+  bool join_before = false;
   LnRowsParams lnr{};   // OP_LNROWS: second half of a sliced convolution
   // debug view of the op's fp16 NHWC output (if any)
   const __half* dbg = nullptr;
@@ -167,6 +171,7 @@ struct Plan {
   size_t shifts_off = 0;
   size_t xstate_off = 0;           // fp32 NCHW sampler state the captured graph works on
   size_t raw_off = 0, raw_bytes = 0;   // fp32 partial tiles of the sliced convolutions (after the arena)
+  size_t raw2_off = 0, raw2_bytes = 0; // same, for side-lane ops (they overlap main-lane sliced convolutions)
   int pack_op = -1, time_op = -1, final_op = -1;
   double flops = 0;
   // captured step graph
@@ -222,6 +227,9 @@ struct cdc_engine {
   // cannot be captured); joined to the caller's stream with events on both sides
   cudaStream_t loop_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t side_stream = nullptr;   // second lane of the step (see Op::lane)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool two_lanes = true;                // CDC_TWO_LANES=0: everything on one stream
   // context state
   bool ctx_set = false;
   int ctx_B = 0, ctx_H = 0, ctx_W = 0;
@@ -636,6 +644,15 @@ struct Builder {
   // ResnetBlock: block1 (+temb shift) -> block2 (+residual). Returns the output activation.
   Act resnet(const std::string& name, const std::vector<SegIn>& segs1, const std::vector<SegIn>& segs_res,
              const ResW& w, int h, int wd, float2* stats_out) {
+    // res_conv first, on the side lane: it only depends on the block input and overlaps block1
+    Act r;
+    bool own_r = false;
+    if (w.has_res) {
+      r = new_act(w.cout, h, wd, true);
+      own_r = true;
+      Op& rop = conv(name + "res_conv", three_pass_in(segs_res), w.res, EPI_BIAS, r, 1, 0);
+      rop.lane = e->two_lanes ? 1 : 0;
+    }
     Act h1 = new_act(w.cout, h, wd);
     {
       Op& op = conv(name + "block1", segs1, w.b1.conv, EPI_LN_SHIFT, h1, 1, 0);
@@ -644,17 +661,11 @@ struct Builder {
       op.conv.shift = ws<float>(pl->shifts_off) + w.shift_off;
       op.conv.shift_stride = e->R;
     }
-    Act r;
-    bool own_r = false;
-    if (w.has_res) {
-      r = new_act(w.cout, h, wd, true);
-      own_r = true;
-      conv(name + "res_conv", three_pass_in(segs_res), w.res, EPI_BIAS, r, 1, 0);
-    }
     Act out = new_act(w.cout, h, wd, true);
     {
       std::vector<SegIn> s2 = {{h1, 3, 3, -1, -1}};
       Op& op = conv(name + "block2", s2, w.b2.conv, EPI_LN_RES, out, 1, 0);
+      op.join_before = w.has_res;
       op.conv.ln_g = dptr<float>(e, w.b2.g);
       op.conv.ln_b = dptr<float>(e, w.b2.b);
       if (w.has_res) {
@@ -908,8 +919,10 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   if (sliceable) {
     const long long out_pix = (long long)B * c.out_H * c.out_W;
     t.raw_split_stride = out_pix * N;
-    t.raw = reinterpret_cast<float*>(pl->ws + pl->raw_off);
-    pl->raw_bytes = std::max(pl->raw_bytes, (size_t)((size_t)t.k_splits * (size_t)out_pix * (size_t)N * 4));
+    const size_t need = (size_t)t.k_splits * (size_t)out_pix * (size_t)N * 4;
+    if (op.lane == 1) pl->raw2_bytes = std::max(pl->raw2_bytes, need);   // raw pointer patched once raw_bytes is final
+    else pl->raw_bytes = std::max(pl->raw_bytes, need);
+    t.raw = nullptr;
   }
   op.tcp = t;
   op.use_tc = true;
@@ -1109,7 +1122,7 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
       fin.name = op.name;
       fin.dbg = op.dbg; fin.dC = op.dC; fin.dH = op.dH; fin.dW = op.dW;
       LnRowsParams& q = fin.lnr;
-      q.raw = op.tcp.raw;
+      q.raw = nullptr;   // patched below
       q.k_splits = op.tcp.k_splits;
       q.split_stride = op.tcp.raw_split_stride;
       q.N = c.Ntot; q.Ntot = c.Ntot;
@@ -1120,6 +1133,7 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
       q.res = c.res; q.res_C0 = c.res_C0; q.res2 = c.res2; q.res_lo = c.res_lo; q.res2_lo = c.res2_lo;
       q.out = c.out; q.out_lo = c.out_lo; q.stats_out = c.stats_out;
       fin.grid = dim3((unsigned)((q.rows + 7) / 8), 1, 1);
+      fin.lane = op.lane;
       op.name += "#partials";
       op.dbg = nullptr;
       fin.flops = 0;
@@ -1133,7 +1147,13 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
       if (pl->ops[i].kind == OP_FINAL) pl->final_op = (int)i;
     }
   }
-  pl->total_bytes = pl->raw_off + pl->raw_bytes;
+  pl->raw2_off = (pl->raw_off + pl->raw_bytes + 255) & ~size_t(255);
+  for (auto& op : pl->ops) {
+    float* rawp = reinterpret_cast<float*>(pl->ws + (op.lane == 1 ? pl->raw2_off : pl->raw_off));
+    if (op.kind == OP_CONV && op.use_tc && op.tcp.epi == EPI_RAW) op.tcp.raw = rawp;
+    if (op.kind == OP_LNROWS) op.lnr.raw = rawp;
+  }
+  pl->total_bytes = pl->raw2_off + pl->raw2_bytes;
   pl->flops = 0;
   for (auto& op : pl->ops) pl->flops += op.flops;
   return 0;
@@ -1259,9 +1279,28 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
 }
 
 int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
+  bool side_busy = false;
   for (size_t i = 0; i < pl->ops.size(); ++i) {
-    int rc = run_op(e, pl, i, a, st);
+    const Op& op = pl->ops[i];
+    cudaStream_t use = st;
+    if (op.lane == 1) {
+      if (!side_busy) {   // fork: the side lane starts after everything enqueued on the main lane so far
+        CUDA_TRY(e, cudaEventRecord(e->ev_fork, st));
+        CUDA_TRY(e, cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+        side_busy = true;
+      }
+      use = e->side_stream;
+    } else if (op.join_before && side_busy) {
+      CUDA_TRY(e, cudaEventRecord(e->ev_join, e->side_stream));
+      CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_join, 0));
+      side_busy = false;
+    }
+    int rc = run_op(e, pl, i, a, use);
     if (rc) return rc;
+  }
+  if (side_busy) {
+    CUDA_TRY(e, cudaEventRecord(e->ev_join, e->side_stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_join, 0));
   }
   if (a.advance) {
     launch_k(advance_step_kernel, dim3(1), dim3(32), 0, st, e->d_step);
@@ -1349,12 +1388,17 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) return fail(nullptr, CDC_ERR_UNSUPPORTED, "device sm_%d%d: this build targets sm_100a only", prop.major, prop.minor);
   if (cudaMalloc(&e->d_step, sizeof(int)) != cudaSuccess) return fail(nullptr, CDC_ERR_CUDA, "cudaMalloc failed");
+  if (cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess)
+    return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   if (cudaStreamCreateWithFlags(&e->loop_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess)
     return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
+  if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
   if (const char* v = getenv("CDC_PDL")) g_pdl = atoi(v) != 0;
   if (const char* v = getenv("CDC_SLICE_SLOTS")) e->slice_slots = std::max(1, atoi(v));
@@ -1374,6 +1418,9 @@ void cdc_engine_destroy(cdc_engine* e) {
   if (e->d_table) cudaFree(e->d_table);
   if (e->d_step) cudaFree(e->d_step);
   if (e->loop_stream) cudaStreamDestroy(e->loop_stream);
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   delete e;
