@@ -292,6 +292,8 @@ struct SegSpec {  // how one K-segment of a conv maps onto the reference's OIHW 
   int mode;       // 0: channel k of chunk cc at tap (ty,tx) <- W[o][coff + cc*64+k][ty][tx]
                   // 1: packed input X0: k = kx*8 + c (c < creal) at vertical tap ty <- W[o][coff + c][ty][kx]  (kw==1)
                   // 2: packed input X0, 1x1 conv: k = 3*8 + c <- W[o][coff + c][0][0]
+                  // 3: like 2, plus the weight remainder fp16(w - fp16(w)) at k = 7*8 + c (X0 carries a second
+                  //    copy of the centre pixel there), so hi and lo weight passes share one K chunk
   int coff;       // first reference input channel of this segment
   int creal;      // real channels (mode 1/2)
   int part = 0;   // 0: fp16(w)   1: fp16(w - fp16(w))  (weight compensation term of the 3-pass trunk convolutions)
@@ -303,6 +305,7 @@ std::vector<SegSpec> three_pass(const std::vector<SegSpec>& base, const std::vec
   for (size_t i = 0; i < base.size(); ++i)
     if (has_lo[i]) out.push_back(base[i]);
   for (size_t i = 0; i < base.size(); ++i) {
+    if (base[i].mode == 3) continue;   // remainder already folded into the same chunk
     SegSpec s = base[i];
     s.part = 1;
     out.push_back(s);
@@ -339,10 +342,10 @@ int pack_conv(cdc_engine* e, const std::string& key, int N, int Cin_ref, int KH,
                 if (kx < KW && c < s.creal) v = w->data[(((size_t)o * Cin_ref + s.coff + c) * KH + ty) * KW + kx];
               } else {
                 const int kx = k >> 3, c = k & 7;
-                if (kx == 3 && c < s.creal) v = w->data[((size_t)o * Cin_ref + s.coff + c)];
+                if ((kx == 3 || (s.mode == 3 && kx == 7)) && c < s.creal) v = w->data[((size_t)o * Cin_ref + s.coff + c)];
               }
               __half hv = __float2half_rn(v);
-              if (s.part == 1) hv = __float2half_rn(v - __half2float(hv));
+              if (s.part == 1 || (s.mode == 3 && (k >> 3) == 7)) hv = __float2half_rn(v - __half2float(hv));
               tmp[((size_t)q * N + o) * 64 + k] = hv;
             }
   }
@@ -575,7 +578,8 @@ struct Builder {
   struct SegIn {
     Act a;
     int kh, kw, dy0, dx0;
-    bool lo = false;  // read the compensation tensor of `a`
+    bool lo = false;        // read the compensation tensor of `a`
+    bool merged = false;    // hi and lo weight passes share this segment's chunks (packed input, SegSpec mode 3)
   };
   // mirror of three_pass() on the activation side: (x_hi, W_hi)..., (x_lo, W_hi) for sources that have lo, (x_hi, W_lo)...
   static std::vector<SegIn> three_pass_in(const std::vector<SegIn>& base) {
@@ -586,7 +590,8 @@ struct Builder {
         t.lo = true;
         out.push_back(t);
       }
-    for (const SegIn& s : base) out.push_back(s);
+    for (const SegIn& s : base)
+      if (!s.merged) out.push_back(s);
     return out;
   }
 
@@ -882,7 +887,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.b_off = 16384;
   t.vr_max = 1;
   t.total_sc = c.total_chunks;
-  const bool vr_ok = e->vreuse && !sliceable && c.stride == 1 && t.TB == 1 && (t.TW == 8 || t.TW == 16) && a_rows == 128;
+  const bool vr_ok = e->vreuse && c.stride == 1 && t.TB == 1 && (t.TW == 8 || t.TW == 16) && a_rows == 128;
   if (vr_ok) {
     int khmax = 1;
     for (int i = 0; i < c.nseg; ++i) khmax = std::max(khmax, c.seg[i].kh);
@@ -903,6 +908,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
       }
     }
   }
+  if (t.k_splits > std::max(1, t.total_sc / 2)) t.k_splits = std::max(1, t.total_sc / 2);
   const int stage_bytes = tc_stage_bytes(t.b_off, t.vr_max, Nc);
   t.stages = std::max(2, std::min(kTcMaxStages, budget / stage_bytes));
   t.phases = c.phases ? 4 : 1;
@@ -1019,7 +1025,7 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     const bool has_ctx = (l < L - 1) && (l < cfg.n_context);
     if (l == 0) {
       s1.push_back({x, 7, 1, -3, 0});
-      sr.push_back({x, 1, 1, 0, 0});
+      sr.push_back({x, 1, 1, 0, 0, false, true});
       if (has_ctx && !e->fold_ctx0) {
         s1.push_back({ctx_act(0), 7, 7, -3, -3});
         sr.push_back({ctx_act(0), 1, 1, 0, 0});
@@ -1470,7 +1476,7 @@ int cdc_engine_finalize(cdc_engine* e) {
     if (l == 0) {
       const int folded = (has_ctx && e->fold_ctx0) ? cc : 0;
       s1.push_back({64, 7, 1, 1, 0, cx + folded});
-      sr.push_back({64, 1, 1, 2, 0, cx + folded});
+      sr.push_back({64, 1, 1, 3, 0, cx + folded});
       if (has_ctx && !e->fold_ctx0) {
         s1.push_back({cc, 7, 7, 0, cx, 0});
         sr.push_back({cc, 1, 1, 0, cx, 0});

@@ -9,7 +9,8 @@ namespace cdc {
 // x_t (fp32 NCHW, `cx` channels) [+ a small fp32 NCHW context with `cc` channels, cx+cc <= 8]
 //   -> X0 [B,H,W,64] fp16 with channel kx*8+c = value at (y, x+kx-3): the horizontal taps of the first
 //   7x7 convolution (unet.py:61 / network_components.py:87) folded into K, so that conv runs as 7
-//   vertical taps of 64 channels.  Slot kx=7 and channels >= cx+cc are zero.
+//   vertical taps of 64 channels.  Slot kx=7 repeats the centre pixel (kx=3): the 1x1 res_conv puts its fp16 weight
+//   remainders there, the 7x7 conv has zero weights for it.  Channels >= cx+cc of every slot are zero.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_input_kernel(const float* __restrict__ x, int cx, const float* __restrict__ ctx, int cc,
                                   int B, int H, int W, __half* __restrict__ out) {
@@ -23,11 +24,11 @@ __global__ void pack_input_kernel(const float* __restrict__ x, int cx, const flo
     const int t = pix / W;
     const int yy = t % H;
     const int b = t / H;
-    const int sx = xx + kx - 3;
+    const int sx = kx < 7 ? xx + kx - 3 : xx;   // slot 7 repeats the centre pixel (weight-remainder pass of res_conv)
     float v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = 0.f;
-    if (kx < 7 && sx >= 0 && sx < W) {
+    if (sx >= 0 && sx < W) {
       const size_t row = (size_t)yy * W + sx;
       const size_t plane = (size_t)H * W;
 #pragma unroll

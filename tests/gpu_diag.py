@@ -102,6 +102,7 @@ def main():
         for kx in range(7):
             lo, hi = max(0, 3 - kx), min(W, W + 3 - kx)
             exp[:, :, lo:hi, kx * 8:kx * 8 + nc] = src[:, :, :, lo + kx - 3:hi + kx - 3].permute(0, 2, 3, 1)
+        exp[:, :, :, 56:56 + nc] = src.permute(0, 2, 3, 1)   # slot 7 = centre copy
         say(f"pack_input maxabs={(got - exp.half().float()).abs().max().item():.3e}")
 
     # ---- DDIM steps: engine (eager per-step API and graph loop) vs oracle driven by the oracle U-Net ----
