@@ -950,17 +950,21 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(A, op %s, seg %d) failed: %d", op.name.c_str(), i, (int)r);
   }
   for (int i = c.nseg; i < kMaxSeg; ++i) op.maps.a[i] = op.maps.a[0];
-  {
-    const cuuint64_t rows = (cuuint64_t)(c.groups > 1 ? B : t.phases) * c.total_chunks * N;
-    cuuint64_t gdim[2] = {64, rows};
-    cuuint64_t gstr[1] = {128};
-    cuuint32_t box[2] = {64, (cuuint32_t)t.n_piece};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&op.maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)c.W, gdim, gstr, box, estr,
+  // Weights [phase | image][chunk q][C_out][64]: per segment a 4-D view {64, kw*cpt*C_out, kh, phase | image} so that
+  // one box {64, n_piece, vr, 1} brings the weight tiles of all vr vertical taps of a (kx, channel chunk).
+  for (int i = 0; i < c.nseg; ++i) {
+    const cuuint64_t tap_rows = (cuuint64_t)c.seg[i].kw * t.seg[i].cpt * N;
+    cuuint64_t gdim[4] = {64, tap_rows, (cuuint64_t)c.seg[i].kh, (cuuint64_t)(c.groups > 1 ? B : t.phases)};
+    cuuint64_t gstr[3] = {128, tap_rows * 128, (cuuint64_t)c.total_chunks * N * 128};
+    cuuint32_t box[4] = {64, (cuuint32_t)t.n_piece, (cuuint32_t)t.seg[i].vr, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    void* wbase = (void*)((const __half*)c.W + (size_t)t.seg[i].q0 * N * 64);
+    CUresult r = enc(&op.maps.b[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, wbase, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(B, op %s) failed: %d", op.name.c_str(), (int)r);
+    if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(B, op %s, seg %d) failed: %d", op.name.c_str(), i, (int)r);
   }
+  for (int i = c.nseg; i < kMaxSeg; ++i) op.maps.b[i] = op.maps.b[0];
   return 0;
 }
 
@@ -1769,7 +1773,14 @@ int cdc_engine_profile_ops(cdc_engine* e, int iters, float* ms_out, double* flop
   CUDA_TRY(e, cudaEventCreate(&b));
   RunArgs args = e->last_args;
   args.advance = false;
+  long long* clkbuf = nullptr;
+  if (getenv("CDC_DBG_CLK")) cudaMallocManaged(&clkbuf, 16 * sizeof(long long));
   for (int i = 0; i < n; ++i) {
+    if (clkbuf) {
+      cudaDeviceSynchronize();
+      for (int k = 0; k < 16; ++k) clkbuf[k] = 0;
+      pl->ops[i].tcp.dbg_clk = clkbuf;
+    }
     int rc = run_op(e, pl, (size_t)i, args, st);  // warm
     if (rc) return rc;
     CUDA_TRY(e, cudaEventRecord(a, st));
@@ -1781,6 +1792,16 @@ int cdc_engine_profile_ops(cdc_engine* e, int iters, float* ms_out, double* flop
     CUDA_TRY(e, cudaEventElapsedTime(&ms, a, b));
     ms_out[i] = ms / iters;
     flops_out[i] = pl->ops[i].flops;
+    if (clkbuf) {
+      cudaDeviceSynchronize();
+      pl->ops[i].tcp.dbg_clk = nullptr;
+      if (pl->ops[i].use_tc && pl->ops[i].kind == OP_CONV) {
+        const double d = iters + 1;
+        fprintf(stderr, "CLK %-28s us=%7.1f prod: tot=%8.0f wait=%8.0f n=%5.1f pro=%6.0f | mma: tot=%8.0f wfull=%8.0f wtempty=%8.0f tiles=%5.1f | epi: tot=%8.0f wtfull=%8.0f pre=%8.0f p12=%8.0f p3=%8.0f\n",
+                pl->ops[i].name.c_str(), ms_out[i] * 1000, clkbuf[0] / d, clkbuf[1] / d, clkbuf[2] / d, clkbuf[12] / d,
+                clkbuf[3] / d, clkbuf[4] / d, clkbuf[5] / d, clkbuf[6] / d, clkbuf[7] / d, clkbuf[8] / d, clkbuf[9] / d, clkbuf[10] / d, clkbuf[11] / d);
+      }
+    }
   }
   cudaEventDestroy(a);
   cudaEventDestroy(b);

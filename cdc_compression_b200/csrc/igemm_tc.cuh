@@ -73,6 +73,7 @@ struct TcConvParams {
   // over n_slices x k_splits CTAs: each computes columns [slice*Nc, +Nc) over a K sub-range and stores its fp32
   // partial tile to raw[k_split][out_pixel][Ntot]; ln_rows_kernel then sums the K partials in a fixed order and
   // applies the fused epilogue (deterministic, no atomics).  Nc == Ntot, n_slices == k_splits == 1 otherwise.
+  long long* dbg_clk;        // profiling aid (CDC_DBG_CLK=1 + cdc_engine_profile_ops): per-role cycle counters of CTA 0
   int Nc;
   int n_slices, k_splits;
   float* raw;
@@ -82,8 +83,8 @@ struct TcConvParams {
 constexpr int EPI_RAW = 4;
 
 struct TcMaps {
-  CUtensorMap a[kMaxSeg];
-  CUtensorMap b;
+  CUtensorMap a[kMaxSeg];   // activations of segment s: {64 channels, W, H, B}
+  CUtensorMap b[kMaxSeg];   // weights of segment s: {64, kw*cpt*C_out, kh, phase | image}
 };
 
 // o[0..8) += residual channels [col, col+8) of pixel pix (hi + optional lo)
@@ -212,6 +213,30 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same instruction with the descriptors given as their low words (start address | LBO) over a shared high word
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -264,8 +289,10 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.nseg; ++i) tc::prefetch_tmap(&maps.a[i]);
-    tc::prefetch_tmap(&maps.b);
+    for (int i = 0; i < p.nseg; ++i) {
+      tc::prefetch_tmap(&maps.a[i]);
+      tc::prefetch_tmap(&maps.b[i]);
+    }
     for (int s = 0; s < p.stages; ++s) {
       tc::mbar_init(bar_full + 8 * s, 1);
       tc::mbar_init(bar_empty + 8 * s, 1);
@@ -291,6 +318,8 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const bool clk = p.dbg_clk != nullptr && blockIdx.x == 0;
+  const long long k_t1 = clock64();
   pdl_wait();   // everything above (barriers, TMEM, constant vectors) overlapped the previous kernel's tail
 
   const int tiles_per_phase = p.tiles_x * p.tiles_y * p.tiles_b;
@@ -300,100 +329,141 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const int t = u / units_per_tile;
-        const int su = u - t * units_per_tile;
-        const int slice = su / p.k_splits, ksp = su - slice * p.k_splits;
-        const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
-        const int ph = t / tiles_per_phase;
-        int r = t - ph * tiles_per_phase;
-        const int tb = r / (p.tiles_x * p.tiles_y);
-        r -= tb * p.tiles_x * p.tiles_y;
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB;
-        const int dyp = p.phases > 1 ? (ph >> 1) - 1 : 0, dxp = p.phases > 1 ? (ph & 1) - 1 : 0;
-        const int wrow0 = ph * p.w_rows_per_phase + b0 * p.w_rows_per_image + slice * N;
-        int sc = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const TcSeg sg = p.seg[s];
-          const CUtensorMap* mA = &maps.a[s];
-          for (int kyo = 0; kyo < sg.kh; kyo += sg.vr)
-            for (int kx = 0; kx < sg.kw; ++kx)
-              for (int cc = 0; cc < sg.cpt; ++cc, ++sc) {
-                if (sc < sc0 || sc >= sc1) continue;
-                tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+    // The whole warp walks the loop converged (uniform control flow keeps the index math in uniform registers);
+    // one elected lane issues the copies.
+    const bool leader = tc::elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    long long c_wait = 0, c_n = 0;
+    const long long c_t0 = clock64();
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int t = u / units_per_tile;
+      const int su = u - t * units_per_tile;
+      const int slice = su / p.k_splits, ksp = su - slice * p.k_splits;
+      const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
+      const int ph = t / tiles_per_phase;
+      int r = t - ph * tiles_per_phase;
+      const int tb = r / (p.tiles_x * p.tiles_y);
+      r -= tb * p.tiles_x * p.tiles_y;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB;
+      const int dyp = p.phases > 1 ? (ph >> 1) - 1 : 0, dxp = p.phases > 1 ? (ph & 1) - 1 : 0;
+      const int wsel = p.phases > 1 ? ph : (p.w_rows_per_image ? b0 : 0);   // weight set: phase | image
+      int sc = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const TcSeg sg = p.seg[s];
+        const CUtensorMap* mA = &maps.a[s];
+        const CUtensorMap* mB = &maps.b[s];
+        const uint32_t tx_bytes = (uint32_t)(sg.a_bytes + sg.vr * N * 128);
+        for (int kyo = 0; kyo < sg.kh; kyo += sg.vr)
+          for (int kx = 0; kx < sg.kw; ++kx)
+            for (int cc = 0; cc < sg.cpt; ++cc, ++sc) {
+              if (sc < sc0 || sc >= sc1) continue;
+              const long long w0 = clock64();
+              tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              c_wait += clock64() - w0;
+              ++c_n;
+              if (leader) {
                 const uint32_t sA = base + stage * stage_bytes;
                 const uint32_t sB = sA + p.b_off;
                 const uint32_t full = bar_full + 8 * stage;
-                tc::mbar_expect_tx(full, (uint32_t)(sg.a_bytes + sg.vr * N * 128));
+                tc::mbar_expect_tx(full, tx_bytes);
                 // one activation box: TH + vr - 1 tile rows starting at the first vertical tap
                 tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp,
                                 y0 * p.stride + kyo + sg.dy0 + dyp, b0);
-                for (int v = 0; v < sg.vr; ++v) {   // the weight tiles of the vr vertical taps it feeds
-                  const int q = sg.q0 + ((kyo + v) * sg.kw + kx) * sg.cpt + cc;
-                  for (int pc = 0; pc < p.n_split; ++pc)
-                    tc::tma_load_2d(sB + (v * p.n_split + pc) * p.n_piece * 128, &maps.b, full, 0,
-                                    wrow0 + q * p.Ntot + pc * p.n_piece);
-                }
-                if (++stage == p.stages) {
-                  stage = 0;
-                  phase ^= 1;
-                }
+                // the weight tiles of the vr vertical taps it feeds: [piece][tap][n_piece rows]
+                for (int pc = 0; pc < p.n_split; ++pc)
+                  tc::tma_load_4d(sB + pc * sg.vr * p.n_piece * 128, mB, full, 0,
+                                  (kx * sg.cpt + cc) * p.Ntot + slice * N + pc * p.n_piece, kyo, wsel);
               }
-        }
+              __syncwarp();
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
       }
+    }
+    if (clk && leader) {
+      p.dbg_clk[0] += clock64() - c_t0;
+      p.dbg_clk[1] += c_wait;
+      p.dbg_clk[2] += c_n;
+      p.dbg_clk[12] += c_t0 - k_t1;
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_f16(p.n_piece);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
-        const int ksp = u % p.k_splits;
-        const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
-        const int buf = it % p.nbuf;
-        const uint32_t use = (uint32_t)(it / p.nbuf);  // how many times this buffer was used before
-        tc::mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
-        tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
-        uint32_t accumulate = 0;
-        int sc = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const int vr = p.seg[s].vr;
-          const int nsc = (p.seg[s].kh / vr) * p.seg[s].kw * p.seg[s].cpt;
-          for (int i = 0; i < nsc; ++i, ++sc) {
-            if (sc < sc0 || sc >= sc1) continue;
-            tc::mbar_wait(bar_full + 8 * stage, phase);
-            tc::tc_fence_after();
-            const uint32_t sA = base + stage * stage_bytes;
-            const uint32_t sB = sA + p.b_off;
-            for (int v = 0; v < vr; ++v) {
-              // vertical tap v reads the same box TW pixel rows (= TW*128 bytes, a multiple of the swizzle atom) down
-              const uint64_t dA = tc::make_desc_sw128(sA + v * p.TW * 128);
+    // Whole warp converged, one elected lane issues (the same lane every time: tcgen05.commit tracks the MMAs of
+    // the thread that executes it).
+    const bool leader = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_f16(p.n_piece);
+    const uint32_t desc_hi = (uint32_t)(tc::make_desc_sw128(0) >> 32);
+    const uint32_t a_vstep = (uint32_t)(p.TW * 128) >> 4;        // one tile row of pixels, in descriptor units
+    const uint32_t b_step = (uint32_t)(p.n_piece * 128) >> 4;    // one weight tile
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    long long c_wf = 0, c_we = 0;
+    const long long c_t0 = clock64();
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      const int ksp = u % p.k_splits;
+      const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
+      const int buf = it % p.nbuf;
+      const uint32_t use = (uint32_t)(it / p.nbuf);  // how many times this buffer was used before
+      const long long w0 = clock64();
+      tc::mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
+      c_we += clock64() - w0;
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+      uint32_t accumulate = 0;
+      int sc = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int vr = p.seg[s].vr;
+        const int nsc = (p.seg[s].kh / vr) * p.seg[s].kw * p.seg[s].cpt;
+        for (int i = 0; i < nsc; ++i, ++sc) {
+          if (sc < sc0 || sc >= sc1) continue;
+          const long long w1 = clock64();
+          tc::mbar_wait(bar_full + 8 * stage, phase);
+          c_wf += clock64() - w1;
+          tc::tc_fence_after();
+          if (leader) {
+            const uint32_t a_lo = (uint32_t)tc::make_desc_sw128(base + stage * stage_bytes);
+            const uint32_t b_lo = a_lo + ((uint32_t)p.b_off >> 4);
+            if (p.n_split == 1) {
+              for (int v = 0; v < vr; ++v) {
+                // vertical tap v reads the same box TW pixel rows (a multiple of the swizzle atom) further down
+                const uint32_t av = a_lo + v * a_vstep, bv = b_lo + v * b_step;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                for (int pc = 0; pc < p.n_split; ++pc) {
-                  const uint64_t dB = tc::make_desc_sw128(sB + (v * p.n_split + pc) * p.n_piece * 128);
-                  tc::umma_f16(d_tmem + pc * p.n_piece, dA + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), idesc,
-                               accumulate);
-                }
-                accumulate = 1;
+                for (int ks = 0; ks < 4; ++ks)
+                  tc::umma_f16_lo(d_tmem, av + ks * 2, bv + ks * 2, desc_hi, idesc,
+                                  (ks == 0 && v == 0) ? accumulate : 1u);
               }
+            } else {
+              for (int v = 0; v < vr; ++v)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  for (int pc = 0; pc < p.n_split; ++pc)
+                    tc::umma_f16_lo(d_tmem + pc * p.n_piece, a_lo + v * a_vstep + ks * 2,
+                                    b_lo + (pc * vr + v) * b_step + ks * 2, desc_hi, idesc,
+                                    (ks == 0 && v == 0) ? accumulate : 1u);
             }
             tc::umma_commit(bar_empty + 8 * stage);  // frees this smem stage once the MMAs above retire
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
-            }
+          }
+          __syncwarp();
+          accumulate = 1;
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        tc::umma_commit(bar_tfull + 8 * buf);  // accumulator of this tile complete
       }
+      if (leader) tc::umma_commit(bar_tfull + 8 * buf);  // accumulator of this tile complete
+      __syncwarp();
+    }
+    if (clk && leader) {
+      p.dbg_clk[3] += clock64() - c_t0;
+      p.dbg_clk[4] += c_wf;
+      p.dbg_clk[5] += c_we;
+      p.dbg_clk[6] += it;
     }
   } else {
     // =============================== epilogue (4 warps, one GEMM row per thread) ===============================
@@ -403,7 +473,10 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
     const float inv_n = 1.f / (float)N;
     int cached_img = -1;                       // image whose affine vectors sit in s_vec[3*384..] (EPI_AFFINE)
     int it = 0;
+    long long c_wt = 0, c_pre = 0, c_p12 = 0, c_p3 = 0;
+    const long long c_t0 = clock64();
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      const long long i0 = clock64();
       const int t = u / units_per_tile;
       const int buf = it % p.nbuf;
       const uint32_t use = (uint32_t)(it / p.nbuf);
@@ -469,7 +542,12 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         }
       }
 
+      const long long w0 = clock64();
       tc::mbar_wait(bar_tfull + 8 * buf, use & 1);
+      const long long e0 = clock64();
+      c_wt += e0 - w0;
+      c_pre += w0 - i0;
+      long long e1 = e0;
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * N);
       uint32_t v[32];
@@ -526,6 +604,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
           }
         }
         const float rstd = 1.f / sqrtf(sq * inv_n + 1e-5f);
+        e1 = clock64();
         const float* shift =
             (EPI == EPI_LN_SHIFT && p.shift && valid) ? p.shift + (size_t)bb * p.shift_stride : nullptr;
         float osum = 0.f, osq = 0.f;
@@ -571,6 +650,15 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       }
       tc::tc_fence_before();
       tc::mbar_arrive(bar_tempty + 8 * buf);
+      c_p12 += e1 - e0;
+      c_p3 += clock64() - e1;
+    }
+    if (clk && threadIdx.x == 64) {
+      p.dbg_clk[10] += c_p12;
+      p.dbg_clk[11] += c_p3;
+      p.dbg_clk[7] += clock64() - c_t0;
+      p.dbg_clk[8] += c_wt;
+      p.dbg_clk[9] += c_pre;
     }
   }
 
