@@ -28,6 +28,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, *NVCC_FLAGS, *[os.path.join(_HERE, s) for s in SOURCES], "-o", out]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("CDC_ROLE_CLK"):
+        cmd.insert(1, "-DCDC_ROLE_CLK")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

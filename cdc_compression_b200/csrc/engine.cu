@@ -522,25 +522,30 @@ cudaError_t launch_igemm(const Op& op, cudaStream_t st) {
   return cudaErrorInvalidValue;
 }
 
-template <int EPI, int OCC>
+template <int EPI, int OCC, bool N64>
 cudaError_t launch_tc_t(const Op& op, cudaStream_t st) {
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(igemm_tc_kernel<EPI, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t err = cudaFuncSetAttribute(igemm_tc_kernel<EPI, OCC, N64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            227 * 1024 / OCC);
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
-  return launch_k(igemm_tc_kernel<EPI, OCC>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st, op.maps, op.tcp);
+  return launch_k(igemm_tc_kernel<EPI, OCC, N64>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st, op.maps, op.tcp);
 }
 
 cudaError_t launch_tc(const Op& op, cudaStream_t st) {
   const int occ = op.tc_occ;
+  const bool ln = op.tcp.epi == EPI_LN_SHIFT || op.tcp.epi == EPI_LN_RES;
+  if (ln && op.tcp.Nc == 64 && occ == 2) {
+    if (op.tcp.epi == EPI_LN_SHIFT) return launch_tc_t<EPI_LN_SHIFT, 2, true>(op, st);
+    return launch_tc_t<EPI_LN_RES, 2, true>(op, st);
+  }
 #define CASE(E_)                                                \
   if (op.tcp.epi == E_) {                                       \
-    return occ == 2 ? launch_tc_t<E_, 2>(op, st) : launch_tc_t<E_, 1>(op, st); \
+    return occ == 2 ? launch_tc_t<E_, 2, false>(op, st) : launch_tc_t<E_, 1, false>(op, st); \
   }
   CASE(EPI_BIAS) CASE(EPI_LN_SHIFT) CASE(EPI_LN_RES) CASE(EPI_AFFINE) CASE(EPI_RAW)
 #undef CASE
@@ -878,7 +883,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.nbuf = (2 * Nc <= 512) ? 2 : 1;
   // Nc <= 128: two CTAs per SM (2 x 256 TMEM columns, half the shared memory each) double the epilogue warps
   int ctas_per_sm = Nc <= 128 ? 2 : 1;
-  auto smem_budget = [](int ctas) { return (227 * 1024) / ctas - 1024 - 5 * 384 * 4 - 256 - (ctas > 1 ? 1024 : 0); };
+  auto smem_budget = [Nc](int ctas) { return (227 * 1024) / ctas - 1024 - tc_tail_bytes(Nc) - (ctas > 1 ? 1024 : 0); };
   int budget = smem_budget(ctas_per_sm);
   // Vertical reuse: one activation box of TH+kh-1 tile rows serves all kh vertical taps of a (kx, channel chunk) —
   // tap ky reads it TW pixel rows further down, which is a whole number of 1024-byte swizzle atoms when TW is
@@ -919,7 +924,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.bias = c.bias; t.ln_g = c.ln_g; t.ln_b = c.ln_b; t.shift = c.shift; t.shift_stride = c.shift_stride;
   t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2; t.res_lo = c.res_lo; t.res2_lo = c.res2_lo;
   t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
-  op.tc_smem = tc_smem_bytes(stage_bytes, t.stages);
+  op.tc_smem = tc_smem_bytes(stage_bytes, t.stages, Nc);
   op.tc_occ = ctas_per_sm;
   op.tc_grid = std::min(tiles_total * t.n_slices * t.k_splits, e->num_sms * ctas_per_sm);
   if (sliceable) {

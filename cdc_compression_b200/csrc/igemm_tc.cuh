@@ -87,53 +87,6 @@ struct TcMaps {
   CUtensorMap b[kMaxSeg];   // weights of segment s: {64, kw*cpt*C_out, kh, phase | image}
 };
 
-// o[0..8) += residual channels [col, col+8) of pixel pix (hi + optional lo)
-__device__ __forceinline__ void add_res8(const TcConvParams& p, long long pix, int col, float (&o)[8]) {
-  const __half* hi;
-  const __half* lo;
-  if (col < p.res_C0) {
-    const size_t off = (size_t)pix * p.res_C0 + col;
-    hi = p.res + off;
-    lo = p.res_lo ? p.res_lo + off : nullptr;
-  } else {
-    const size_t off = (size_t)pix * (p.Ntot - p.res_C0) + (col - p.res_C0);
-    hi = p.res2 + off;
-    lo = p.res2_lo ? p.res2_lo + off : nullptr;
-  }
-  uint4 rr = *reinterpret_cast<const uint4*>(hi);
-  float2 f;
-  f = unpack_half2(rr.x); o[0] += f.x; o[1] += f.y;
-  f = unpack_half2(rr.y); o[2] += f.x; o[3] += f.y;
-  f = unpack_half2(rr.z); o[4] += f.x; o[5] += f.y;
-  f = unpack_half2(rr.w); o[6] += f.x; o[7] += f.y;
-  if (lo) {
-    rr = *reinterpret_cast<const uint4*>(lo);
-    f = unpack_half2(rr.x); o[0] += f.x; o[1] += f.y;
-    f = unpack_half2(rr.y); o[2] += f.x; o[3] += f.y;
-    f = unpack_half2(rr.z); o[4] += f.x; o[5] += f.y;
-    f = unpack_half2(rr.w); o[6] += f.x; o[7] += f.y;
-  }
-}
-// store 8 channels as fp16 (+ rounding remainders into out_lo); returns the stored hi halves
-__device__ __forceinline__ uint4 store_out8(const TcConvParams& p, size_t off, const float (&o)[8]) {
-  uint4 w;
-  w.x = pack_half2(o[0], o[1]);
-  w.y = pack_half2(o[2], o[3]);
-  w.z = pack_half2(o[4], o[5]);
-  w.w = pack_half2(o[6], o[7]);
-  *reinterpret_cast<uint4*>(p.out + off) = w;
-  if (p.out_lo) {
-    uint4 l;
-    float2 f;
-    f = unpack_half2(w.x); l.x = pack_half2(o[0] - f.x, o[1] - f.y);
-    f = unpack_half2(w.y); l.y = pack_half2(o[2] - f.x, o[3] - f.y);
-    f = unpack_half2(w.z); l.z = pack_half2(o[4] - f.x, o[5] - f.y);
-    f = unpack_half2(w.w); l.w = pack_half2(o[6] - f.x, o[7] - f.y);
-    *reinterpret_cast<uint4*>(p.out_lo + off) = l;
-  }
-  return w;
-}
-
 namespace tc {
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -157,8 +110,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a pipeline bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 6000000000LL) {  // ~3 s at 1.9 GHz
@@ -167,6 +119,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -253,19 +209,143 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// issue-only variant (pair with tmem_wait_ld) so that several loads are in flight before the single wait
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): halves the instruction count of the epilogue arithmetic.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 pku(uint32_t a, uint32_t b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ float2 upk(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 }  // namespace tc
+
+// Role cycle counters (profiling aid, see TcConvParams::dbg_clk) cost ~10 % of the epilogue's stall samples: compiled in
+// only with -DCDC_ROLE_CLK (CDC_ROLE_CLK=1 python -m cdc_compression_b200.build).
+#ifdef CDC_ROLE_CLK
+#define CDC_CLK() clock64()
+#else
+#define CDC_CLK() 0LL
+#endif
 
 constexpr int kTcThreads = 192;
 constexpr int kTcMaxStages = 8;
 
-// dynamic smem: [stages][A 16 KB | B Ntot*128 B] (1024-aligned) + epilogue vectors + barriers
+// Epilogue staging: every epilogue warp owns a 2 KB transposition buffer (32 rows x 64 bytes) and a table of its 32
+// rows' output pixel indices, so that global loads / stores of the epilogue are issued row-contiguously (8 rows x 64
+// bytes per warp instruction) instead of one 16-byte piece per thread at a row-sized stride.
+constexpr int kEpiStageBytes = 2048;
+constexpr int kEpiPixBytes = 32 * 8;
+// bytes after the pipeline stages: epilogue vectors (bias | g | b: 3 x Nc floats), barriers, staging, pixel tables, and
+// per epilogue warp 2 x Nc floats for the per-image vectors (timestep shift | attention affine u, c)
+__host__ __device__ inline int tc_tail_bytes(int Nc) {
+  return 3 * Nc * 4 + 256 + 4 * (kEpiStageBytes + kEpiPixBytes) + 4 * (2 * Nc * 4);
+}
+// dynamic smem: [stages][A box | B tiles] (1024-aligned) + tail
 __host__ __device__ inline int tc_stage_bytes(int b_off, int vr_max, int Nc) { return b_off + vr_max * Nc * 128; }
-__host__ __device__ inline int tc_smem_bytes(int stage_bytes, int stages) {
-  return 1024 /*alignment slack*/ + stages * stage_bytes + 5 * 384 * 4 + 256;
+__host__ __device__ inline int tc_smem_bytes(int stage_bytes, int stages, int Nc) {
+  return 1024 /*alignment slack*/ + stages * stage_bytes + tc_tail_bytes(Nc);
+}
+
+// byte offset of 16-byte chunk `chunk` (0..3) of 64-byte row `row` in a staging buffer (XOR swizzle: conflict-free for
+// both the row-per-lane and the 4-lanes-per-row access patterns)
+__device__ __forceinline__ uint32_t stg_off(int row, int chunk) {
+  return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+// Every lane holds the 64 bytes w[0..3] of ITS row; row r goes to dst + pix[r] * row_bytes (skipped when pix[r] < 0).
+__device__ __forceinline__ void warp_store_rows64(uint8_t* stg, const long long* pixtab, int lane, const uint4 (&w)[4],
+                                                  uint8_t* dst, long long row_bytes) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = w[j];
+  __syncwarp();
+  uint4 v[4];
+  long long px[4];
+  const int ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {   // all shared-memory reads first, so that their latencies overlap
+    const int row = i * 8 + (lane >> 2);
+    v[i] = *reinterpret_cast<const uint4*>(stg + stg_off(row, ch));
+    px[i] = pixtab[row];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (px[i] >= 0) *reinterpret_cast<uint4*>(dst + px[i] * row_bytes + ch * 16) = v[i];
+  __syncwarp();
+}
+// Row-contiguous loads of 32 rows x 64 bytes (4 lanes per row); the data lands in the loading lanes' registers ...
+__device__ __forceinline__ void warp_load_rows64(const long long* pixtab, int lane, uint4 (&r)[4], const uint8_t* src,
+                                                 long long row_bytes) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2), ch = lane & 3;
+    const long long px = pixtab[row];
+    r[i] = px >= 0 ? *reinterpret_cast<const uint4*>(src + px * row_bytes + ch * 16) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+// ... and is transposed through the staging buffer so that r[0..3] become the 64 bytes of the lane's OWN row.
+__device__ __forceinline__ void warp_rows64_to_own(uint8_t* stg, int lane, uint4 (&r)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + stg_off(i * 8 + (lane >> 2), lane & 3)) = r[i];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
+  __syncwarp();
+}
+// 8 fp32 values -> 8 fp16 (hi) and the fp16 rounding remainders (lo)
+__device__ __forceinline__ void pack_out8(const float (&o)[8], uint4& hi, uint4& lo, bool want_lo) {
+  hi.x = pack_half2(o[0], o[1]);
+  hi.y = pack_half2(o[2], o[3]);
+  hi.z = pack_half2(o[4], o[5]);
+  hi.w = pack_half2(o[6], o[7]);
+  if (!want_lo) return;
+  float2 f;
+  f = unpack_half2(hi.x); lo.x = pack_half2(o[0] - f.x, o[1] - f.y);
+  f = unpack_half2(hi.y); lo.y = pack_half2(o[2] - f.x, o[3] - f.y);
+  f = unpack_half2(hi.z); lo.z = pack_half2(o[4] - f.x, o[5] - f.y);
+  f = unpack_half2(hi.w); lo.w = pack_half2(o[6] - f.x, o[7] - f.y);
 }
 
 // EPI: fused epilogue (compile-time, prunes the others); OCC: CTAs per SM the register budget is sized for.
-template <int EPI, int OCC>
+// N64: LayerNorm epilogue specialised for C_out == 64 (row held in registers, single TMEM pass).
+template <int EPI, int OCC, bool N64>
 __global__ void __launch_bounds__(kTcThreads, OCC)
 igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -273,8 +353,10 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int stage_bytes = tc_stage_bytes(p.b_off, p.vr_max, p.Nc);
-  float* s_vec = reinterpret_cast<float*>(smem + p.stages * stage_bytes);  // bias | g | b | (u | c): 5 x 384
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + 5 * 384 * 4);
+  const int vs = p.Nc;                                                     // stride of the epilogue vectors
+  float* s_vec = reinterpret_cast<float*>(smem + p.stages * stage_bytes);  // bias | g | b: 3 x Nc
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + 3 * vs * 4);
+  uint8_t* s_stage = smem + p.stages * stage_bytes + 3 * vs * 4 + 256;     // 4 x kEpiStageBytes, 4 pixel tables, 4 x 2Nc floats
   // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2]; then the TMEM base address word
   const uint32_t bar_full = smem_u32(s_bar);
   const uint32_t bar_empty = bar_full + 8 * kTcMaxStages;
@@ -311,15 +393,15 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   // epilogue vectors -> smem (all threads)
   for (int i = threadIdx.x; i < (EPI == EPI_RAW ? 0 : N); i += kTcThreads) {
     s_vec[i] = p.bias ? p.bias[i] : 0.f;
-    s_vec[384 + i] = p.ln_g ? p.ln_g[i] : 1.f;
-    s_vec[768 + i] = p.ln_b ? p.ln_b[i] : 0.f;
+    s_vec[vs + i] = p.ln_g ? p.ln_g[i] : 1.f;
+    s_vec[2 * vs + i] = p.ln_b ? p.ln_b[i] : 0.f;
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const bool clk = p.dbg_clk != nullptr && blockIdx.x == 0;
-  const long long k_t1 = clock64();
+  const long long k_t1 = CDC_CLK();
   pdl_wait();   // everything above (barriers, TMEM, constant vectors) overlapped the previous kernel's tail
 
   const int tiles_per_phase = p.tiles_x * p.tiles_y * p.tiles_b;
@@ -335,7 +417,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
     int stage = 0;
     uint32_t phase = 0;
     long long c_wait = 0, c_n = 0;
-    const long long c_t0 = clock64();
+    const long long c_t0 = CDC_CLK();
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int t = u / units_per_tile;
       const int su = u - t * units_per_tile;
@@ -359,9 +441,9 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
           for (int kx = 0; kx < sg.kw; ++kx)
             for (int cc = 0; cc < sg.cpt; ++cc, ++sc) {
               if (sc < sc0 || sc >= sc1) continue;
-              const long long w0 = clock64();
+              const long long w0 = CDC_CLK();
               tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              c_wait += clock64() - w0;
+              c_wait += CDC_CLK() - w0;
               ++c_n;
               if (leader) {
                 const uint32_t sA = base + stage * stage_bytes;
@@ -385,7 +467,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       }
     }
     if (clk && leader) {
-      p.dbg_clk[0] += clock64() - c_t0;
+      p.dbg_clk[0] += CDC_CLK() - c_t0;
       p.dbg_clk[1] += c_wait;
       p.dbg_clk[2] += c_n;
       p.dbg_clk[12] += c_t0 - k_t1;
@@ -403,15 +485,15 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
     uint32_t phase = 0;
     int it = 0;
     long long c_wf = 0, c_we = 0;
-    const long long c_t0 = clock64();
+    const long long c_t0 = CDC_CLK();
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
       const int ksp = u % p.k_splits;
       const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
       const int buf = it % p.nbuf;
       const uint32_t use = (uint32_t)(it / p.nbuf);  // how many times this buffer was used before
-      const long long w0 = clock64();
+      const long long w0 = CDC_CLK();
       tc::mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
-      c_we += clock64() - w0;
+      c_we += CDC_CLK() - w0;
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
       uint32_t accumulate = 0;
@@ -421,9 +503,9 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         const int nsc = (p.seg[s].kh / vr) * p.seg[s].kw * p.seg[s].cpt;
         for (int i = 0; i < nsc; ++i, ++sc) {
           if (sc < sc0 || sc >= sc1) continue;
-          const long long w1 = clock64();
+          const long long w1 = CDC_CLK();
           tc::mbar_wait(bar_full + 8 * stage, phase);
-          c_wf += clock64() - w1;
+          c_wf += CDC_CLK() - w1;
           tc::tc_fence_after();
           if (leader) {
             const uint32_t a_lo = (uint32_t)tc::make_desc_sw128(base + stage * stage_bytes);
@@ -460,7 +542,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       __syncwarp();
     }
     if (clk && leader) {
-      p.dbg_clk[3] += clock64() - c_t0;
+      p.dbg_clk[3] += CDC_CLK() - c_t0;
       p.dbg_clk[4] += c_wf;
       p.dbg_clk[5] += c_we;
       p.dbg_clk[6] += it;
@@ -471,12 +553,21 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
     const int row = quad * 32 + lane;          // GEMM row == TMEM lane
     const int lx = row % p.TW, ly = (row / p.TW) % p.TH, lb = row / (p.TW * p.TH);
     const float inv_n = 1.f / (float)N;
-    int cached_img = -1;                       // image whose affine vectors sit in s_vec[3*384..] (EPI_AFFINE)
+    uint8_t* stg = s_stage + (warp - 2) * kEpiStageBytes;
+    long long* pixtab = reinterpret_cast<long long*>(s_stage + 4 * kEpiStageBytes) + (warp - 2) * 32;
+    const long long out_rb = (long long)N * 2;          // bytes per output pixel row (N == Ntot outside sliced mode)
+    const bool has_res = p.res != nullptr && (EPI != EPI_LN_SHIFT) && (EPI != EPI_RAW);
+    const bool has_lo = p.out_lo != nullptr;
+    // per-image vectors (timestep shift of the tile's image | attention affine u, c): warp-private copy, fetched with
+    // cp.async at the top of the tile so that its latency hides behind the accumulator wait
+    float* wvec = reinterpret_cast<float*>(s_stage + 4 * (kEpiStageBytes + kEpiPixBytes)) + (warp - 2) * 2 * vs;
+    constexpr bool shift_smem = false;   // measured: slower than reading the L1-resident shift row directly (+15 us at level 0)
+    int cached_img = -1;                       // image whose vectors sit in wvec
     int it = 0;
     long long c_wt = 0, c_pre = 0, c_p12 = 0, c_p3 = 0;
-    const long long c_t0 = clock64();
+    const long long c_t0 = CDC_CLK();
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
-      const long long i0 = clock64();
+      const long long i0 = CDC_CLK();
       const int t = u / units_per_tile;
       const int buf = it % p.nbuf;
       const uint32_t use = (uint32_t)(it / p.nbuf);
@@ -490,29 +581,40 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       const int py = p.phases > 1 ? (ph >> 1) : 0, px = p.phases > 1 ? (ph & 1) : 0;
       const long long opix =
           valid ? ((long long)bb * p.out_H + yy * p.out_sy + py) * p.out_W + xx * p.out_sx + px : 0;
-      const size_t obase = (size_t)opix * N;
-      const bool has_res = p.res != nullptr && (EPI != EPI_LN_SHIFT) && (EPI != EPI_RAW);
+      __syncwarp();
+      pixtab[lane] = valid ? opix : -1;
+      __syncwarp();
 
-      // residual prefetch (hi / lo halves of 32 channels) — issued ahead of the TMEM waits that would expose it
+      // residual prefetch (hi / lo halves of 32 channels of 32 rows, row-contiguous) — issued ahead of the TMEM waits
+      // that would expose it; transposed to one-row-per-lane through the staging buffer right before use
       uint4 rh[4], rl[4];
       auto prefetch_res = [&](int c0) {
-        if (!(has_res && valid)) return;
+        if (!has_res) return;
         const __half* hi;
         const __half* lo;
+        long long rb;
         if (c0 < p.res_C0) {
-          const size_t off = (size_t)opix * p.res_C0 + c0;
-          hi = p.res + off;
-          lo = p.res_lo ? p.res_lo + off : nullptr;
+          rb = (long long)p.res_C0 * 2;
+          hi = p.res + c0;
+          lo = p.res_lo ? p.res_lo + c0 : nullptr;
         } else {
-          const size_t off = (size_t)opix * (N - p.res_C0) + (c0 - p.res_C0);
-          hi = p.res2 + off;
-          lo = p.res2_lo ? p.res2_lo + off : nullptr;
+          rb = (long long)(N - p.res_C0) * 2;
+          hi = p.res2 + (c0 - p.res_C0);
+          lo = p.res2_lo ? p.res2_lo + (c0 - p.res_C0) : nullptr;
         }
+        warp_load_rows64(pixtab, lane, rh, reinterpret_cast<const uint8_t*>(hi), rb);
+        if (lo) {
+          warp_load_rows64(pixtab, lane, rl, reinterpret_cast<const uint8_t*>(lo), rb);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          rh[j] = reinterpret_cast<const uint4*>(hi)[j];
-          rl[j] = lo ? reinterpret_cast<const uint4*>(lo)[j] : make_uint4(0u, 0u, 0u, 0u);
+          for (int j = 0; j < 4; ++j) rl[j] = make_uint4(0u, 0u, 0u, 0u);
         }
+      };
+      auto own_res = [&](int c0) {   // uniform per warp
+        if (!has_res) return;
+        warp_rows64_to_own(stg, lane, rh);
+        const bool lo = c0 < p.res_C0 ? p.res_lo != nullptr : p.res2_lo != nullptr;
+        if (lo) warp_rows64_to_own(stg, lane, rl);
       };
       auto add_res = [&](int j, float (&o)[8]) {  // j = 8-channel group inside the prefetched 32
         float2 f;
@@ -528,119 +630,262 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       prefetch_res(0);
 
       float2 st = make_float2(0.f, 1.f);
-      if (EPI == EPI_AFFINE) {
-        if (valid) st = p.stats_in[opix];
-        const int img = tb * p.TB;  // TB == 1 for per-image (attention) weights: one image per tile
-        if (img != cached_img) {    // uniform across the 4 epilogue warps
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int i = threadIdx.x - 64; i < N; i += 128) {
-            s_vec[3 * 384 + i] = p.aff_u[(size_t)img * N + i];
-            s_vec[4 * 384 + i] = p.aff_c[(size_t)img * N + i];
+      if (EPI == EPI_AFFINE || shift_smem) {
+        if (EPI == EPI_AFFINE && valid) st = p.stats_in[opix];
+        const int img = min(tb * p.TB, p.B - 1);  // TB == 1: one image per tile
+        if (img != cached_img) {                  // uniform across the warp
+          if (EPI == EPI_AFFINE) {
+            for (int i = lane * 4; i < N; i += 128) {
+              cp_async16(smem_u32(wvec + i), p.aff_u + (size_t)img * N + i, 16);
+              cp_async16(smem_u32(wvec + vs + i), p.aff_c + (size_t)img * N + i, 16);
+            }
+          } else {
+            for (int i = lane * 4; i < N; i += 128)
+              cp_async16(smem_u32(wvec + i), p.shift + (size_t)img * p.shift_stride + i, 16);
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          cp_async_commit();
           cached_img = img;
         }
       }
 
-      const long long w0 = clock64();
+      const long long w0 = CDC_CLK();
       tc::mbar_wait(bar_tfull + 8 * buf, use & 1);
-      const long long e0 = clock64();
+      const long long e0 = CDC_CLK();
       c_wt += e0 - w0;
       c_pre += w0 - i0;
       long long e1 = e0;
       tc::tc_fence_after();
+      if (EPI == EPI_AFFINE || shift_smem) {
+        cp_async_wait<0>();
+        __syncwarp();
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * N);
       uint32_t v[32];
+      uint8_t* const out_b = reinterpret_cast<uint8_t*>(p.out);
+      uint8_t* const out_lo_b = reinterpret_cast<uint8_t*>(p.out_lo);
 
       if (EPI == EPI_RAW) {
         const int su = u - t * units_per_tile;
         const int slice = su / p.k_splits, ksp = su - slice * p.k_splits;
-        float* dst = p.raw + (size_t)ksp * p.raw_split_stride + (size_t)opix * p.Ntot + slice * N;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.raw + (size_t)ksp * p.raw_split_stride + slice * N);
+        const long long raw_rb = (long long)p.Ntot * 4;
         for (int c0 = 0; c0 < N; c0 += 32) {
           tc::tmem_ld32(taddr + c0, v);
-          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<uint4*>(dst + c0)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int h = 0; h < 2; ++h) {
+            uint4 w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              w[j] = make_uint4(v[h * 16 + 4 * j], v[h * 16 + 4 * j + 1], v[h * 16 + 4 * j + 2], v[h * 16 + 4 * j + 3]);
+            warp_store_rows64(stg, pixtab, lane, w, dst + (c0 + h * 16) * 4, raw_rb);
           }
         }
       } else if (EPI == EPI_BIAS || EPI == EPI_AFFINE) {
+        using tc::f32x2;
+        const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(s_vec);            // conv bias
+        const ulonglong2* vu = reinterpret_cast<const ulonglong2*>(wvec);        // affine u (per image)
+        const ulonglong2* vc = reinterpret_cast<const ulonglong2*>(wvec + vs);   // affine c (per image)
+        const f32x2 nmean2 = tc::pk(-st.x, -st.x), rstd2 = tc::pk(st.y, st.y);
         for (int c0 = 0; c0 < N; c0 += 32) {
           tc::tmem_ld32(taddr + c0, v);
+          if (c0 + 32 >= N) {   // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
+            tc::tc_fence_before();
+            tc::mbar_arrive(bar_tempty + 8 * buf);
+          }
+          own_res(c0);
+          uint4 wh[4], wl[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float o[8];
+            f32x2 y[4];
+            const int q = (c0 >> 2) + 2 * j;
             if (EPI == EPI_AFFINE) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int c = c0 + j * 8 + k;
-                o[k] = st.y * (__uint_as_float(v[j * 8 + k]) - st.x * s_vec[3 * 384 + c]) + s_vec[4 * 384 + c];
-              }
+              const ulonglong2 u0 = vu[q], u1 = vu[q + 1], a0 = vc[q], a1 = vc[q + 1];
+              y[0] = tc::fma2(rstd2, tc::fma2(nmean2, u0.x, tc::pku(v[8 * j], v[8 * j + 1])), a0.x);
+              y[1] = tc::fma2(rstd2, tc::fma2(nmean2, u0.y, tc::pku(v[8 * j + 2], v[8 * j + 3])), a0.y);
+              y[2] = tc::fma2(rstd2, tc::fma2(nmean2, u1.x, tc::pku(v[8 * j + 4], v[8 * j + 5])), a1.x);
+              y[3] = tc::fma2(rstd2, tc::fma2(nmean2, u1.y, tc::pku(v[8 * j + 6], v[8 * j + 7])), a1.y);
             } else {
+              const ulonglong2 b0 = vb[q], b1 = vb[q + 1];
+              y[0] = tc::add2(tc::pku(v[8 * j], v[8 * j + 1]), b0.x);
+              y[1] = tc::add2(tc::pku(v[8 * j + 2], v[8 * j + 3]), b0.y);
+              y[2] = tc::add2(tc::pku(v[8 * j + 4], v[8 * j + 5]), b1.x);
+              y[3] = tc::add2(tc::pku(v[8 * j + 6], v[8 * j + 7]), b1.y);
+            }
+            float o[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(v[j * 8 + k]) + s_vec[c0 + j * 8 + k];
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = tc::upk(y[k]);
+              o[2 * k] = f.x;
+              o[2 * k + 1] = f.y;
             }
             if (has_res) add_res(j, o);
-            if (valid) store_out8(p, obase + c0 + j * 8, o);
+            pack_out8(o, wh[j], wl[j], has_lo);
           }
           if (c0 + 32 < N) prefetch_res(c0 + 32);
+          warp_store_rows64(stg, pixtab, lane, wh, out_b + c0 * 2, out_rb);
+          if (has_lo) warp_store_rows64(stg, pixtab, lane, wl, out_lo_b + c0 * 2, out_rb);
         }
       } else {
-        // ---- channel LayerNorm: exact two-pass statistics from the fp32 accumulator ----
-        float sum = 0.f;
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          tc::tmem_ld32(taddr + c0, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]) + s_vec[c0 + j];
-        }
-        const float mean = sum * inv_n;
-        float sq = 0.f;
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          tc::tmem_ld32(taddr + c0, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(v[j]) + s_vec[c0 + j] - mean;
-            sq += d * d;
-          }
-        }
-        const float rstd = 1.f / sqrtf(sq * inv_n + 1e-5f);
-        e1 = clock64();
-        const float* shift =
-            (EPI == EPI_LN_SHIFT && p.shift && valid) ? p.shift + (size_t)bb * p.shift_stride : nullptr;
+        // ---- channel LayerNorm: exact two-pass statistics from the fp32 accumulator (packed fp32x2 arithmetic) ----
+        using tc::f32x2;
+        const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(s_vec);            // conv bias
+        const ulonglong2* vg = reinterpret_cast<const ulonglong2*>(s_vec + vs);       // LayerNorm gain
+        const ulonglong2* vo = reinterpret_cast<const ulonglong2*>(s_vec + 2 * vs);   // LayerNorm offset
+        const ulonglong2* shift2 =
+            shift_smem ? reinterpret_cast<const ulonglong2*>(wvec)
+                       : (EPI == EPI_LN_SHIFT && p.shift)
+                             ? reinterpret_cast<const ulonglong2*>(p.shift + (size_t)(valid ? bb : 0) * p.shift_stride)
+                             : nullptr;
         float osum = 0.f, osq = 0.f;
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          float4 sh[8];
-          if (shift) {
+        float mean, rstd;
+        // finish 8 columns [c, c+8) of the row from their centred values d[0..3] (pairs) -> fp16 hi / lo pieces
+        auto finish8 = [&](const f32x2 (&d)[4], int c, int j, uint4& hi, uint4& lo, f32x2 rstd2) {
+          const ulonglong2 g0 = vg[c >> 2], g1 = vg[(c >> 2) + 1], b0 = vo[c >> 2], b1 = vo[(c >> 2) + 1];
+          f32x2 y[4];
+          y[0] = tc::fma2(d[0], tc::mul2(rstd2, g0.x), b0.x);
+          y[1] = tc::fma2(d[1], tc::mul2(rstd2, g0.y), b0.y);
+          y[2] = tc::fma2(d[2], tc::mul2(rstd2, g1.x), b1.x);
+          y[3] = tc::fma2(d[3], tc::mul2(rstd2, g1.y), b1.y);
+          float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sh[j] = reinterpret_cast<const float4*>(shift + c0)[j];
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = tc::upk(y[k]);
+            o[2 * k] = fmaxf(f.x, 0.f);
+            o[2 * k + 1] = fmaxf(f.y, 0.f);
           }
-          tc::tmem_ld32(taddr + c0, v);
+          if (shift2) {
+            const ulonglong2 s0 = shift2[c >> 2], s1 = shift2[(c >> 2) + 1];
+            float2 f;
+            f = tc::upk(tc::add2(tc::pk(o[0], o[1]), s0.x)); o[0] = f.x; o[1] = f.y;
+            f = tc::upk(tc::add2(tc::pk(o[2], o[3]), s0.y)); o[2] = f.x; o[3] = f.y;
+            f = tc::upk(tc::add2(tc::pk(o[4], o[5]), s1.x)); o[4] = f.x; o[5] = f.y;
+            f = tc::upk(tc::add2(tc::pk(o[6], o[7]), s1.y)); o[6] = f.x; o[7] = f.y;
+          }
+          if (has_res) add_res(j, o);
+          pack_out8(o, hi, lo, has_lo);
+          if (p.stats_out) {  // statistics of the rounded values the consumer will read
+            float2 f;
+            f = unpack_half2(hi.x); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+            f = unpack_half2(hi.y); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+            f = unpack_half2(hi.z); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+            f = unpack_half2(hi.w); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+          }
+        };
+        if (N64) {
+          // the whole row lives in registers: one TMEM pass, and the accumulator buffer is released before the arithmetic
+          uint32_t v1[32];
+          tc::tmem_ld32_issue(taddr, v);
+          tc::tmem_ld32_issue(taddr + 32, v1);
+          tc::tmem_wait_ld();
+          tc::tc_fence_before();
+          tc::mbar_arrive(bar_tempty + 8 * buf);
+          f32x2 x[32];
+          f32x2 s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float o[8];
+          for (int i = 0; i < 8; ++i) {
+            const ulonglong2 ba = vb[i], bc = vb[8 + i];
+            x[2 * i] = tc::add2(tc::pku(v[4 * i], v[4 * i + 1]), ba.x);
+            x[2 * i + 1] = tc::add2(tc::pku(v[4 * i + 2], v[4 * i + 3]), ba.y);
+            x[16 + 2 * i] = tc::add2(tc::pku(v1[4 * i], v1[4 * i + 1]), bc.x);
+            x[16 + 2 * i + 1] = tc::add2(tc::pku(v1[4 * i + 2], v1[4 * i + 3]), bc.y);
+            s0 = tc::add2(s0, x[2 * i]);
+            s1 = tc::add2(s1, x[2 * i + 1]);
+            s2 = tc::add2(s2, x[16 + 2 * i]);
+            s3 = tc::add2(s3, x[16 + 2 * i + 1]);
+          }
+          {
+            const float2 f = tc::upk(tc::add2(tc::add2(s0, s1), tc::add2(s2, s3)));
+            mean = (f.x + f.y) * inv_n;
+          }
+          const f32x2 nm = tc::pk(-mean, -mean);
+          f32x2 q0 = 0ull, q1 = 0ull, q2 = 0ull, q3 = 0ull;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int c = c0 + j * 8 + k;
-              const float y = (__uint_as_float(v[j * 8 + k]) + s_vec[c] - mean) * rstd * s_vec[384 + c] + s_vec[768 + c];
-              o[k] = fmaxf(y, 0.f);
+          for (int i = 0; i < 8; ++i) {
+            x[4 * i] = tc::add2(x[4 * i], nm);
+            x[4 * i + 1] = tc::add2(x[4 * i + 1], nm);
+            x[4 * i + 2] = tc::add2(x[4 * i + 2], nm);
+            x[4 * i + 3] = tc::add2(x[4 * i + 3], nm);
+            q0 = tc::fma2(x[4 * i], x[4 * i], q0);
+            q1 = tc::fma2(x[4 * i + 1], x[4 * i + 1], q1);
+            q2 = tc::fma2(x[4 * i + 2], x[4 * i + 2], q2);
+            q3 = tc::fma2(x[4 * i + 3], x[4 * i + 3], q3);
+          }
+          {
+            const float2 f = tc::upk(tc::add2(tc::add2(q0, q1), tc::add2(q2, q3)));
+            rstd = 1.f / sqrtf((f.x + f.y) * inv_n + 1e-5f);
+          }
+          e1 = CDC_CLK();
+          const f32x2 rstd2 = tc::pk(rstd, rstd);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int c0 = g * 32;
+            own_res(c0);
+            uint4 wh[4], wl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const f32x2 d[4] = {x[g * 16 + j * 4], x[g * 16 + j * 4 + 1], x[g * 16 + j * 4 + 2], x[g * 16 + j * 4 + 3]};
+              finish8(d, c0 + j * 8, j, wh[j], wl[j], rstd2);
             }
-            if (shift) {
-              o[0] += sh[2 * j].x; o[1] += sh[2 * j].y; o[2] += sh[2 * j].z; o[3] += sh[2 * j].w;
-              o[4] += sh[2 * j + 1].x; o[5] += sh[2 * j + 1].y; o[6] += sh[2 * j + 1].z; o[7] += sh[2 * j + 1].w;
-            }
-            if (has_res) add_res(j, o);
-            if (valid) {
-              const uint4 w = store_out8(p, obase + c0 + j * 8, o);
-              if (p.stats_out) {  // statistics of the rounded values the consumer will read
-                float2 f;
-                f = unpack_half2(w.x); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
-                f = unpack_half2(w.y); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
-                f = unpack_half2(w.z); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
-                f = unpack_half2(w.w); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
-              }
+            if (g == 0) prefetch_res(32);
+            warp_store_rows64(stg, pixtab, lane, wh, out_b + c0 * 2, out_rb);
+            if (has_lo) warp_store_rows64(stg, pixtab, lane, wl, out_lo_b + c0 * 2, out_rb);
+          }
+        } else {
+          f32x2 s0 = 0ull, s1 = 0ull;
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            tc::tmem_ld32(taddr + c0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const ulonglong2 ba = vb[(c0 >> 2) + i];
+              s0 = tc::add2(s0, tc::add2(tc::pku(v[4 * i], v[4 * i + 1]), ba.x));
+              s1 = tc::add2(s1, tc::add2(tc::pku(v[4 * i + 2], v[4 * i + 3]), ba.y));
             }
           }
-          if (c0 + 32 < N) prefetch_res(c0 + 32);
+          {
+            const float2 f = tc::upk(tc::add2(s0, s1));
+            mean = (f.x + f.y) * inv_n;
+          }
+          const f32x2 nm = tc::pk(-mean, -mean);
+          f32x2 q0 = 0ull, q1 = 0ull;
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            tc::tmem_ld32(taddr + c0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const ulonglong2 ba = vb[(c0 >> 2) + i];
+              const f32x2 d0 = tc::add2(tc::add2(tc::pku(v[4 * i], v[4 * i + 1]), ba.x), nm);
+              const f32x2 d1 = tc::add2(tc::add2(tc::pku(v[4 * i + 2], v[4 * i + 3]), ba.y), nm);
+              q0 = tc::fma2(d0, d0, q0);
+              q1 = tc::fma2(d1, d1, q1);
+            }
+          }
+          {
+            const float2 f = tc::upk(tc::add2(q0, q1));
+            rstd = 1.f / sqrtf((f.x + f.y) * inv_n + 1e-5f);
+          }
+          e1 = CDC_CLK();
+          const f32x2 rstd2 = tc::pk(rstd, rstd);
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            tc::tmem_ld32(taddr + c0, v);
+            if (c0 + 32 >= N) {   // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
+              tc::tc_fence_before();
+              tc::mbar_arrive(bar_tempty + 8 * buf);
+            }
+            own_res(c0);
+            uint4 wh[4], wl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const ulonglong2 ba = vb[(c0 >> 2) + 2 * j], bc = vb[(c0 >> 2) + 2 * j + 1];
+              f32x2 d[4];
+              d[0] = tc::add2(tc::add2(tc::pku(v[8 * j], v[8 * j + 1]), ba.x), nm);
+              d[1] = tc::add2(tc::add2(tc::pku(v[8 * j + 2], v[8 * j + 3]), ba.y), nm);
+              d[2] = tc::add2(tc::add2(tc::pku(v[8 * j + 4], v[8 * j + 5]), bc.x), nm);
+              d[3] = tc::add2(tc::add2(tc::pku(v[8 * j + 6], v[8 * j + 7]), bc.y), nm);
+              finish8(d, c0 + j * 8, j, wh[j], wl[j], rstd2);
+            }
+            if (c0 + 32 < N) prefetch_res(c0 + 32);
+            warp_store_rows64(stg, pixtab, lane, wh, out_b + c0 * 2, out_rb);
+            if (has_lo) warp_store_rows64(stg, pixtab, lane, wl, out_lo_b + c0 * 2, out_rb);
+          }
         }
         if (p.stats_out && valid) {
           const float m = osum * inv_n;
@@ -648,15 +893,17 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
           p.stats_out[opix] = make_float2(m, 1.f / sqrtf(var + 1e-5f));
         }
       }
-      tc::tc_fence_before();
-      tc::mbar_arrive(bar_tempty + 8 * buf);
+      if (EPI == EPI_RAW) {
+        tc::tc_fence_before();
+        tc::mbar_arrive(bar_tempty + 8 * buf);
+      }
       c_p12 += e1 - e0;
-      c_p3 += clock64() - e1;
+      c_p3 += CDC_CLK() - e1;
     }
     if (clk && threadIdx.x == 64) {
       p.dbg_clk[10] += c_p12;
       p.dbg_clk[11] += c_p3;
-      p.dbg_clk[7] += clock64() - c_t0;
+      p.dbg_clk[7] += CDC_CLK() - c_t0;
       p.dbg_clk[8] += c_wt;
       p.dbg_clk[9] += c_pre;
     }
