@@ -203,6 +203,7 @@ struct cdc_engine {
   int num_sms = 148;
   int vreuse = 1;      // CDC_VREUSE: 0 off, 1 when it fits the default occupancy, 2 also at one CTA per SM
   bool sliced = true;  // CDC_SLICED=0 disables the sliced low-resolution mode (A/B measurements)
+  bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
   int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
   // derived structure
   std::vector<int> dims, cdims;
@@ -482,18 +483,34 @@ int pack_attn(cdc_engine* e, const std::string& p, int C, AttnW* out) {
 bool g_pdl = false;  // programmatic dependent launch (CDC_PDL=1 enables): measured 2.6 % SLOWER inside the step graph
 
 template <typename... KArgs, typename... Args>
-cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+cudaError_t launch_kc(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                      Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (g_pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {   // thread-block cluster along x (sliced LayerNorm convolutions)
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_kc(kern, grid, block, smem, st, 0, std::forward<Args>(args)...);
 }
 
 template <int BM, int BN, int EPI>
@@ -528,18 +545,20 @@ cudaError_t launch_tc_t(const Op& op, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
+    // OCC only sizes the register budget; a launch may still ask for a whole SM's shared memory (one CTA per SM)
     cudaError_t err = cudaFuncSetAttribute(igemm_tc_kernel<EPI, OCC, N64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           227 * 1024 / OCC);
+                                           227 * 1024);
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
-  return launch_k(igemm_tc_kernel<EPI, OCC, N64>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st, op.maps, op.tcp);
+  return launch_kc(igemm_tc_kernel<EPI, OCC, N64>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st,
+                   op.tcp.cluster_n, op.maps, op.tcp);
 }
 
 cudaError_t launch_tc(const Op& op, cudaStream_t st) {
   const int occ = op.tc_occ;
   const bool ln = op.tcp.epi == EPI_LN_SHIFT || op.tcp.epi == EPI_LN_RES;
-  if (ln && op.tcp.Nc == 64 && occ == 2) {
+  if (ln && op.tcp.Nc == 64) {
     if (op.tcp.epi == EPI_LN_SHIFT) return launch_tc_t<EPI_LN_SHIFT, 2, true>(op, st);
     return launch_tc_t<EPI_LN_RES, 2, true>(op, st);
   }
@@ -870,7 +889,24 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   const int tiles_nominal = ((h * w * 8 + 127) / 128) * (c.phases ? 4 : 1);
   t.Nc = N; t.n_slices = 1; t.k_splits = 1;
   const bool sliceable = e->sliced && c.groups == 1 && op.epi != EPI_AFFINE && tiles_nominal < kSlicedMaxTiles && N >= 128;
-  if (sliceable) {
+  // Fused column slices (default): no K split, the fused epilogue runs in the kernel; LayerNorm epilogues exchange
+  // their row statistics inside a thread-block cluster of the n_slices CTAs of a tile (<= 8: portable cluster size).
+  const bool ln_epi = op.epi == EPI_LN_SHIFT || op.epi == EPI_LN_RES;
+  // Taken when the tile x slice grid alone gives enough CTAs (measured: >= 64 units, 128 for the 4-phase transposed
+  // convolutions); the lowest levels keep the K-split + ln_rows_kernel form, and so do the stride-2 convolutions.
+  const int units_nominal = tiles_nominal * (N / 64);
+  const bool fused = sliceable && e->nslice && N / 64 <= 8 && c.stride == 1 && units_nominal >= (c.phases ? 128 : 64);
+  t.cluster_n = 0;
+  t.xchg_stats = 0;
+  if (fused) {
+    t.Nc = 64;
+    t.n_slices = N / 64;
+    t.k_splits = 1;
+    if (ln_epi) {
+      t.cluster_n = t.n_slices;
+      t.xchg_stats = c.stats_out != nullptr;
+    }
+  } else if (sliceable) {
     t.Nc = 64;
     t.n_slices = N / 64;
     const int slots = e->slice_slots;
@@ -883,7 +919,12 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.nbuf = (2 * Nc <= 512) ? 2 : 1;
   // Nc <= 128: two CTAs per SM (2 x 256 TMEM columns, half the shared memory each) double the epilogue warps
   int ctas_per_sm = Nc <= 128 ? 2 : 1;
-  auto smem_budget = [Nc](int ctas) { return (227 * 1024) / ctas - 1024 - tc_tail_bytes(Nc) - (ctas > 1 ? 1024 : 0); };
+  // few CTAs (lowest levels): one CTA per SM with the deepest pipeline — the K loop is TMA-latency bound there
+  if (fused && tiles_total * t.n_slices <= e->num_sms) ctas_per_sm = 1;
+  const int xsets = t.cluster_n > 1 ? (t.xchg_stats ? 2 : 1) : 0;
+  auto smem_budget = [&](int ctas) {
+    return (227 * 1024) / ctas - 1024 - tc_tail_bytes(Nc, t.cluster_n, xsets) - (ctas > 1 ? 1024 : 0);
+  };
   int budget = smem_budget(ctas_per_sm);
   // Vertical reuse: one activation box of TH+kh-1 tile rows serves all kh vertical taps of a (kx, channel chunk) —
   // tap ky reads it TW pixel rows further down, which is a whole number of 1024-byte swizzle atoms when TW is
@@ -919,15 +960,17 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.phases = c.phases ? 4 : 1;
   t.w_rows_per_phase = c.total_chunks * N;
   t.w_rows_per_image = c.groups > 1 ? c.total_chunks * N : 0;
-  t.epi = sliceable ? EPI_RAW : op.epi;
+  t.epi = (sliceable && !fused) ? EPI_RAW : op.epi;
   t.out = c.out; t.out_lo = c.out_lo; t.out_H = c.out_H; t.out_W = c.out_W; t.out_sy = c.out_sy; t.out_sx = c.out_sx;
   t.bias = c.bias; t.ln_g = c.ln_g; t.ln_b = c.ln_b; t.shift = c.shift; t.shift_stride = c.shift_stride;
   t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2; t.res_lo = c.res_lo; t.res2_lo = c.res2_lo;
   t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
-  op.tc_smem = tc_smem_bytes(stage_bytes, t.stages, Nc);
+  op.tc_smem = tc_smem_bytes(stage_bytes, t.stages, Nc, t.cluster_n, xsets);
   op.tc_occ = ctas_per_sm;
   op.tc_grid = std::min(tiles_total * t.n_slices * t.k_splits, e->num_sms * ctas_per_sm);
-  if (sliceable) {
+  if (fused)   // whole tiles per pass: the grid is a multiple of n_slices, so blockIdx % n_slices is the CTA's column slice
+    op.tc_grid = std::min(tiles_total, std::max(1, (e->num_sms * ctas_per_sm) / t.n_slices)) * t.n_slices;
+  if (sliceable && !fused) {
     const long long out_pix = (long long)B * c.out_H * c.out_W;
     t.raw_split_stride = out_pix * N;
     const size_t need = (size_t)t.k_splits * (size_t)out_pix * (size_t)N * 4;
@@ -945,7 +988,8 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     const cuuint64_t ws_ = (cuuint64_t)c.Ws, hs_ = (cuuint64_t)c.Hs;
     cuuint64_t gdim[4] = {Cs, ws_, hs_, (cuuint64_t)B};
     cuuint64_t gstr[3] = {Cs * 2, ws_ * Cs * 2, hs_ * ws_ * Cs * 2};
-    // strided convolution: the box spans stride*T source pixels, of which every stride-th is loaded
+    // strided convolution: the box spans stride*T source pixels, of which every stride-th is loaded (a dense 5-D
+    // parity view of the source was measured: no faster)
     const cuuint32_t sx = (cuuint32_t)c.stride;
     cuuint32_t box[4] = {64, (cuuint32_t)t.TW * sx, (cuuint32_t)(t.TH + t.seg[i].vr - 1) * sx, (cuuint32_t)t.TB};
     cuuint32_t estr[4] = {1, sx, sx, 1};
@@ -1413,6 +1457,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
     return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
+  if (const char* v = getenv("CDC_NSLICE")) e->nslice = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
   if (const char* v = getenv("CDC_PDL")) g_pdl = atoi(v) != 0;

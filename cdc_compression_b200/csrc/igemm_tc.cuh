@@ -76,6 +76,12 @@ struct TcConvParams {
   long long* dbg_clk;        // profiling aid (CDC_DBG_CLK=1 + cdc_engine_profile_ops): per-role cycle counters of CTA 0
   int Nc;
   int n_slices, k_splits;
+  // Fused column slices (epi != EPI_RAW, n_slices > 1, k_splits == 1): the CTA with blockIdx % n_slices == s computes
+  // columns [s*Nc, +Nc) of every tile it visits with the fused epilogue.  For the LayerNorm epilogues the n_slices CTAs
+  // of a tile form a thread-block cluster (cluster_n == n_slices) and exchange per-row partial statistics through
+  // distributed shared memory (st.async + mbarrier), so no fp32 partial tile ever goes to HBM.
+  int cluster_n;
+  int xchg_stats;            // second exchange for stats_out (row statistics of the stored LayerNorm output)
   float* raw;
   long long raw_split_stride;
 };
@@ -209,6 +215,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- thread-block cluster helpers (distributed shared memory exchange of the sliced LayerNorm statistics) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// 8-byte remote store that signals the destination CTA's mbarrier with its byte count
+__device__ __forceinline__ void st_async_f2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "r"(remote_bar)
+               : "memory");
+}
+
 // issue-only variant (pair with tmem_wait_ld) so that several loads are in flight before the single wait
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -276,13 +303,15 @@ constexpr int kEpiStageBytes = 2048;
 constexpr int kEpiPixBytes = 32 * 8;
 // bytes after the pipeline stages: epilogue vectors (bias | g | b: 3 x Nc floats), barriers, staging, pixel tables, and
 // per epilogue warp 2 x Nc floats for the per-image vectors (timestep shift | attention affine u, c)
-__host__ __device__ inline int tc_tail_bytes(int Nc) {
-  return 3 * Nc * 4 + 256 + 4 * (kEpiStageBytes + kEpiPixBytes) + 4 * (2 * Nc * 4);
+// + cluster exchange buffers: [sets][2 (tile parity)][cluster_n][128 rows] float2
+__host__ __device__ inline int tc_xchg_bytes(int cluster_n, int sets) { return sets * 2 * cluster_n * 128 * 8; }
+__host__ __device__ inline int tc_tail_bytes(int Nc, int cluster_n = 0, int xchg_sets = 0) {
+  return 3 * Nc * 4 + 256 + 4 * (kEpiStageBytes + kEpiPixBytes) + 4 * (2 * Nc * 4) + tc_xchg_bytes(cluster_n, xchg_sets);
 }
 // dynamic smem: [stages][A box | B tiles] (1024-aligned) + tail
 __host__ __device__ inline int tc_stage_bytes(int b_off, int vr_max, int Nc) { return b_off + vr_max * Nc * 128; }
-__host__ __device__ inline int tc_smem_bytes(int stage_bytes, int stages, int Nc) {
-  return 1024 /*alignment slack*/ + stages * stage_bytes + tc_tail_bytes(Nc);
+__host__ __device__ inline int tc_smem_bytes(int stage_bytes, int stages, int Nc, int cluster_n = 0, int xchg_sets = 0) {
+  return 1024 /*alignment slack*/ + stages * stage_bytes + tc_tail_bytes(Nc, cluster_n, xchg_sets);
 }
 
 // byte offset of 16-byte chunk `chunk` (0..3) of 64-byte row `row` in a staging buffer (XOR swizzle: conflict-free for
@@ -363,9 +392,14 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   const uint32_t bar_tfull = bar_empty + 8 * kTcMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kTcMaxStages + 4);
+  const uint32_t bar_x = bar_full + 8 * 24;   // cluster exchange barriers: [set][parity]
+  float2* s_xchg = reinterpret_cast<float2*>(s_stage + 4 * (kEpiStageBytes + kEpiPixBytes) + 4 * (2 * vs * 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.Nc;   // accumulator columns owned by this CTA (== Ntot unless sliced)
+  // fused column slice of this CTA (constant: the grid is a multiple of n_slices, units are tile-major / slice-minor)
+  const bool fused_slice = EPI != EPI_RAW && p.n_slices > 1;
+  const int col0 = fused_slice ? (int)(blockIdx.x % p.n_slices) * N : 0;
   int tmem_cols = 32;
   while (tmem_cols < p.nbuf * N) tmem_cols <<= 1;
 
@@ -383,6 +417,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       tc::mbar_init(bar_tfull + 8 * b, 1);
       tc::mbar_init(bar_tempty + 8 * b, 128);
     }
+    for (int b = 0; b < 4; ++b) tc::mbar_init(bar_x + 8 * b, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
@@ -392,13 +427,14 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
   }
   // epilogue vectors -> smem (all threads)
   for (int i = threadIdx.x; i < (EPI == EPI_RAW ? 0 : N); i += kTcThreads) {
-    s_vec[i] = p.bias ? p.bias[i] : 0.f;
-    s_vec[vs + i] = p.ln_g ? p.ln_g[i] : 1.f;
-    s_vec[2 * vs + i] = p.ln_b ? p.ln_b[i] : 0.f;
+    s_vec[i] = p.bias ? p.bias[col0 + i] : 0.f;
+    s_vec[vs + i] = p.ln_g ? p.ln_g[col0 + i] : 1.f;
+    s_vec[2 * vs + i] = p.ln_b ? p.ln_b[col0 + i] : 0.f;
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  if (p.cluster_n > 1) tc::cluster_sync_all();   // every peer's exchange barriers are initialised before anyone signals them
   const uint32_t tmem_base = *s_tmem;
   const bool clk = p.dbg_clk != nullptr && blockIdx.x == 0;
   const long long k_t1 = CDC_CLK();
@@ -552,10 +588,10 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // GEMM row == TMEM lane
     const int lx = row % p.TW, ly = (row / p.TW) % p.TH, lb = row / (p.TW * p.TH);
-    const float inv_n = 1.f / (float)N;
+    const float inv_n = 1.f / (float)p.Ntot;
     uint8_t* stg = s_stage + (warp - 2) * kEpiStageBytes;
     long long* pixtab = reinterpret_cast<long long*>(s_stage + 4 * kEpiStageBytes) + (warp - 2) * 32;
-    const long long out_rb = (long long)N * 2;          // bytes per output pixel row (N == Ntot outside sliced mode)
+    const long long out_rb = (long long)(EPI == EPI_RAW ? N : p.Ntot) * 2;   // bytes per output pixel row
     const bool has_res = p.res != nullptr && (EPI != EPI_LN_SHIFT) && (EPI != EPI_RAW);
     const bool has_lo = p.out_lo != nullptr;
     // per-image vectors (timestep shift of the tile's image | attention affine u, c): warp-private copy, fetched with
@@ -593,14 +629,15 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         const __half* hi;
         const __half* lo;
         long long rb;
-        if (c0 < p.res_C0) {
+        const int ca = col0 + c0;   // absolute output column
+        if (ca < p.res_C0) {
           rb = (long long)p.res_C0 * 2;
-          hi = p.res + c0;
-          lo = p.res_lo ? p.res_lo + c0 : nullptr;
+          hi = p.res + ca;
+          lo = p.res_lo ? p.res_lo + ca : nullptr;
         } else {
-          rb = (long long)(N - p.res_C0) * 2;
-          hi = p.res2 + (c0 - p.res_C0);
-          lo = p.res2_lo ? p.res2_lo + (c0 - p.res_C0) : nullptr;
+          rb = (long long)(p.Ntot - p.res_C0) * 2;
+          hi = p.res2 + (ca - p.res_C0);
+          lo = p.res2_lo ? p.res2_lo + (ca - p.res_C0) : nullptr;
         }
         warp_load_rows64(pixtab, lane, rh, reinterpret_cast<const uint8_t*>(hi), rb);
         if (lo) {
@@ -613,7 +650,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       auto own_res = [&](int c0) {   // uniform per warp
         if (!has_res) return;
         warp_rows64_to_own(stg, lane, rh);
-        const bool lo = c0 < p.res_C0 ? p.res_lo != nullptr : p.res2_lo != nullptr;
+        const bool lo = col0 + c0 < p.res_C0 ? p.res_lo != nullptr : p.res2_lo != nullptr;
         if (lo) warp_rows64_to_own(stg, lane, rl);
       };
       auto add_res = [&](int j, float (&o)[8]) {  // j = 8-channel group inside the prefetched 32
@@ -661,8 +698,8 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * N);
       uint32_t v[32];
-      uint8_t* const out_b = reinterpret_cast<uint8_t*>(p.out);
-      uint8_t* const out_lo_b = reinterpret_cast<uint8_t*>(p.out_lo);
+      uint8_t* const out_b = reinterpret_cast<uint8_t*>(p.out + col0);
+      uint8_t* const out_lo_b = reinterpret_cast<uint8_t*>(p.out_lo + col0);
 
       if (EPI == EPI_RAW) {
         const int su = u - t * units_per_tile;
@@ -734,7 +771,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         const ulonglong2* shift2 =
             shift_smem ? reinterpret_cast<const ulonglong2*>(wvec)
                        : (EPI == EPI_LN_SHIFT && p.shift)
-                             ? reinterpret_cast<const ulonglong2*>(p.shift + (size_t)(valid ? bb : 0) * p.shift_stride)
+                             ? reinterpret_cast<const ulonglong2*>(p.shift + (size_t)(valid ? bb : 0) * p.shift_stride + col0)
                              : nullptr;
         float osum = 0.f, osq = 0.f;
         float mean, rstd;
@@ -793,9 +830,11 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
             s2 = tc::add2(s2, x[16 + 2 * i]);
             s3 = tc::add2(s3, x[16 + 2 * i + 1]);
           }
+          float lsum;
           {
             const float2 f = tc::upk(tc::add2(tc::add2(s0, s1), tc::add2(s2, s3)));
-            mean = (f.x + f.y) * inv_n;
+            lsum = f.x + f.y;
+            mean = lsum * (1.f / 64.f);   // mean of this CTA's 64 columns
           }
           const f32x2 nm = tc::pk(-mean, -mean);
           f32x2 q0 = 0ull, q1 = 0ull, q2 = 0ull, q3 = 0ull;
@@ -810,10 +849,39 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
             q2 = tc::fma2(x[4 * i + 2], x[4 * i + 2], q2);
             q3 = tc::fma2(x[4 * i + 3], x[4 * i + 3], q3);
           }
+          float m2;   // sum of squared deviations from the (slice) mean
           {
             const float2 f = tc::upk(tc::add2(tc::add2(q0, q1), tc::add2(q2, q3)));
-            rstd = 1.f / sqrtf((f.x + f.y) * inv_n + 1e-5f);
+            m2 = f.x + f.y;
           }
+          if (p.cluster_n > 1) {
+            // Row statistics over all column slices: every CTA of the cluster sends (sum, M2) of its 64 columns to every
+            // peer; the slices are merged in rank order (Chan's parallel variance: exact, deterministic).
+            const int par = it & 1;
+            const uint32_t xb = bar_x + 8 * par;
+            const uint32_t my_rank = blockIdx.x % p.cluster_n;
+            float2* xs = s_xchg + (size_t)par * p.cluster_n * 128;
+            if (row == 0) tc::mbar_expect_tx(xb, (uint32_t)p.cluster_n * 128u * 8u);
+            const uint32_t slot = smem_u32(xs + my_rank * 128 + row);
+            for (int r = 0; r < p.cluster_n; ++r) tc::st_async_f2(tc::mapa(slot, r), lsum, m2, tc::mapa(xb, r));
+            tc::mbar_wait(xb, (uint32_t)(it >> 1) & 1u);
+            float tot = 0.f;
+            for (int r = 0; r < p.cluster_n; ++r) tot += xs[r * 128 + row].x;
+            const float gmean = tot * inv_n;
+            float gm2 = 0.f;
+            for (int r = 0; r < p.cluster_n; ++r) {
+              const float2 f = xs[r * 128 + row];
+              const float dm = f.x * (1.f / 64.f) - gmean;
+              gm2 += f.y + 64.f * dm * dm;
+            }
+            const float dl = mean - gmean;   // re-centre the registers on the row mean
+            const f32x2 dl2 = tc::pk(dl, dl);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = tc::add2(x[i], dl2);
+            mean = gmean;
+            m2 = gm2;
+          }
+          rstd = 1.f / sqrtf(m2 * inv_n + 1e-5f);
           e1 = CDC_CLK();
           const f32x2 rstd2 = tc::pk(rstd, rstd);
 #pragma unroll
@@ -887,7 +955,24 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
             if (has_lo) warp_store_rows64(stg, pixtab, lane, wl, out_lo_b + c0 * 2, out_rb);
           }
         }
-        if (p.stats_out && valid) {
+        if (N64 && p.cluster_n > 1 && p.xchg_stats) {   // row statistics of the stored output over all column slices
+          const int par = it & 1;
+          const uint32_t xb = bar_x + 8 * (2 + par);
+          const uint32_t my_rank = blockIdx.x % p.cluster_n;
+          float2* xs = s_xchg + (size_t)(2 + par) * p.cluster_n * 128;
+          if (row == 0) tc::mbar_expect_tx(xb, (uint32_t)p.cluster_n * 128u * 8u);
+          const uint32_t slot = smem_u32(xs + my_rank * 128 + row);
+          for (int r = 0; r < p.cluster_n; ++r) tc::st_async_f2(tc::mapa(slot, r), osum, osq, tc::mapa(xb, r));
+          tc::mbar_wait(xb, (uint32_t)(it >> 1) & 1u);
+          osum = 0.f;
+          osq = 0.f;
+          for (int r = 0; r < p.cluster_n; ++r) {
+            const float2 f = xs[r * 128 + row];
+            osum += f.x;
+            osq += f.y;
+          }
+        }
+        if (p.stats_out && valid && col0 == 0) {
           const float m = osum * inv_n;
           const float var = fmaxf(osq * inv_n - m * m, 0.f);
           p.stats_out[opix] = make_float2(m, 1.f / sqrtf(var + 1e-5f));
