@@ -8,7 +8,7 @@
 //
 // attn_ctx_kernel   : one pass over x per (image, pixel chunk, 64x64 block of ctx): K/V GEMM,
 //                     online softmax over pixels, P^T V accumulation; writes split partials.
-// attn_combine_kernel, sgemm_tn_kernel, attn_finish_kernel : per-image C x C algebra (fp32).
+// attn_combine_kernel, gemm3xtf32_tn_kernel, attn_finish_kernel : per-image C x C algebra (fp32-grade, 3xTF32 MMAs).
 // The final GEMM (out = M_b-folded weights applied to raw x) runs in the generic conv kernel
 // with EPI_AFFINE and per-image weights.
 #pragma once
@@ -332,84 +332,112 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_ctx, const fl
   }
 }
 
-// Batched fp32 GEMM  Cout[b][m][n] = sum_k At[b][k][m] * Bm[b][k][n]   (M % TM == 0, N % 64 == 0, K % 16 == 0).
-// TM x 64 output tile per CTA, (TM/16) x 4 register tile per thread, K stepped by 16 with register prefetch of the
-// next slab.  fp32 throughout: these are the per-image C x C products behind M_b = W_out ctx^T (C^-1/2 W_q).
-template <int TM>
-__global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ At, const float* __restrict__ Bm,
-                                                       float* __restrict__ Cout, int M, int N, int K,
-                                                       long long sA, long long sB, long long sC) {
-  constexpr int RM = TM / 16;            // rows per thread
-  constexpr int AV = TM * 16 / 4 / 256;  // float4 loads of the A slab per thread
-  __shared__ __align__(16) float As[2][16][TM];
-  __shared__ __align__(16) float Bs[2][16][64];
+// Batched GEMM  Cout[b][m][n] = sum_k At[b][k][m] * Bm[b][k][n]   (M % 64 == 0, N % 64 == 0, K % 16 == 0) with fp32
+// inputs and outputs on the tensor cores: every operand is split into a TF32 "big" part and a TF32 remainder
+// (x = big + small, |small| <= 2^-11 |x|) and the product is accumulated as small*big + big*small + big*big in fp32
+// ("3xTF32": relative error ~1e-6, i.e. fp32-grade — single-pass TF32/fp16 here costs 1e-4 on the U-Net output).
+// These are the per-image C x C products behind M_b = W_out ctx^T (C^-1/2 W_q).
+// 64 x 64 tile per CTA, 4 warps of 32 x 32 (mma.sync m16n8k8), K slabs of 32 in a 3-stage cp.async ring (the K loop
+// is L2-latency bound: 12 slabs at C = 384).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& small) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(big) : "f"(x));
+  const float r = x - __uint_as_float(big);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(small) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct Gemm3xSmem {
+  static constexpr int kLD = 72;      // padded row (floats): fragment loads hit 32 distinct banks
+  static constexpr int kSlab = 32;    // K per pipeline stage (K % 32 == 0: C is a multiple of 64)
+  static constexpr int kStages = 3;
+  static constexpr int kBytes = 2 * kStages * kSlab * kLD * 4;
+};
+
+__global__ void __launch_bounds__(128) gemm3xtf32_tn_kernel(const float* __restrict__ At, const float* __restrict__ Bm,
+                                                            float* __restrict__ Cout, int M, int N, int K,
+                                                            long long sA, long long sB, long long sC) {
+  constexpr int LD = Gemm3xSmem::kLD, KS = Gemm3xSmem::kSlab, ST = Gemm3xSmem::kStages;
+  extern __shared__ __align__(16) uint8_t gsm[];
+  float (*As)[KS][LD] = reinterpret_cast<float (*)[KS][LD]>(gsm);
+  float (*Bs)[KS][LD] = reinterpret_cast<float (*)[KS][LD]>(gsm + ST * KS * LD * 4);
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.z;
   At += (size_t)b * sA;
   Bm += (size_t)b * sB;
   Cout += (size_t)b * sC;
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[RM][4];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int g = lane >> 2, q = lane & 3;
+  float acc[2][4][4];
 #pragma unroll
-  for (int i = 0; i < RM; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float4 ra[AV], rb;
-  auto gload = [&](int k0) {
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int v = 0; v < AV; ++v) {
-      const int idx = tid + v * 256;                 // float4 index inside the 16 x TM slab
-      const int kk = idx / (TM / 4), mm = (idx - kk * (TM / 4)) * 4;
-      ra[v] = *reinterpret_cast<const float4*>(At + (size_t)(k0 + kk) * M + m0 + mm);
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+  auto load = [&](int k0, int buf) {
+#pragma unroll
+    for (int v = 0; v < KS / 8; ++v) {
+      const int idx = tid + v * 128;          // 16-byte piece inside the KS x 64 slab
+      const int kk = idx >> 4, c = (idx & 15) * 4;
+      cp_async16(smem_u32(&As[buf][kk][c]), At + (size_t)(k0 + kk) * M + m0 + c, 16);
+      cp_async16(smem_u32(&Bs[buf][kk][c]), Bm + (size_t)(k0 + kk) * N + n0 + c, 16);
     }
-    const int kk = tid >> 4, nn = (tid & 15) * 4;
-    rb = *reinterpret_cast<const float4*>(Bm + (size_t)(k0 + kk) * N + n0 + nn);
   };
-  auto sstore = [&](int buf) {
+  const int slabs = K / KS;
 #pragma unroll
-    for (int v = 0; v < AV; ++v) {
-      const int idx = tid + v * 256;
-      const int kk = idx / (TM / 4), mm = (idx - kk * (TM / 4)) * 4;
-      *reinterpret_cast<float4*>(&As[buf][kk][mm]) = ra[v];
-    }
-    *reinterpret_cast<float4*>(&Bs[buf][tid >> 4][(tid & 15) * 4]) = rb;
-  };
-  gload(0);
-  sstore(0);
-  __syncthreads();
-  int buf = 0;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    const bool more = k0 + 16 < K;
-    if (more) gload(k0 + 16);
+  for (int i = 0; i < ST - 1; ++i) {
+    if (i < slabs) load(i * KS, i);
+    cp_async_commit();
+  }
+  for (int sidx = 0; sidx < slabs; ++sidx) {
+    const int buf = sidx % ST;
+    cp_async_wait<ST - 2>();
+    __syncthreads();   // slab sidx landed for everyone; everyone finished reading slab sidx - 1
+    if (sidx + ST - 1 < slabs) load((sidx + ST - 1) * KS, (sidx + ST - 1) % ST);
+    cp_async_commit();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[RM];
+    for (int ks = 0; ks < KS / 8; ++ks) {
+      const int k0 = ks * 8;
+      uint32_t ab[2][4], as[2][4];
 #pragma unroll
-      for (int i = 0; i < RM; i += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(&As[buf][kk][ty * RM + i]);
-        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      for (int mt = 0; mt < 2; ++mt) {
+        const int m = wm + mt * 16 + g;
+        split_tf32(As[buf][k0 + q][m], ab[mt][0], as[mt][0]);
+        split_tf32(As[buf][k0 + q][m + 8], ab[mt][1], as[mt][1]);
+        split_tf32(As[buf][k0 + q + 4][m], ab[mt][2], as[mt][2]);
+        split_tf32(As[buf][k0 + q + 4][m + 8], ab[mt][3], as[mt][3]);
       }
-      const float4 bb = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
 #pragma unroll
-      for (int i = 0; i < RM; ++i) {
-        acc[i][0] = fmaf(a[i], bb.x, acc[i][0]);
-        acc[i][1] = fmaf(a[i], bb.y, acc[i][1]);
-        acc[i][2] = fmaf(a[i], bb.z, acc[i][2]);
-        acc[i][3] = fmaf(a[i], bb.w, acc[i][3]);
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = wn + nt * 8 + g;
+        uint32_t bb0, bs0, bb1, bs1;
+        split_tf32(Bs[buf][k0 + q][n], bb0, bs0);
+        split_tf32(Bs[buf][k0 + q + 4][n], bb1, bs1);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_tf32(acc[mt][nt], as[mt], bb0, bb1);   // small terms first
+          mma_tf32(acc[mt][nt], ab[mt], bs0, bs1);
+          mma_tf32(acc[mt][nt], ab[mt], bb0, bb1);
+        }
       }
-    }
-    if (more) {
-      sstore(buf ^ 1);
-      __syncthreads();
-      buf ^= 1;
     }
   }
 #pragma unroll
-  for (int i = 0; i < RM; ++i)
-    *reinterpret_cast<float4*>(Cout + (size_t)(m0 + ty * RM + i) * N + n0 + tx * 4) =
-        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int m = m0 + wm + mt * 16 + g, n = n0 + wn + nt * 8 + q * 2;
+      *reinterpret_cast<float2*>(Cout + (size_t)m * N + n) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(Cout + (size_t)(m + 8) * N + n) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
 }
 
 // Per (image, output row o): Mg16 = half(M[o][:] * g), um = rowsum(float(Mg16)), cm = M[o][:].b_ln + b_out[o].

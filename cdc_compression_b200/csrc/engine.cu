@@ -767,7 +767,7 @@ struct Builder {
       op.kind = OP_SGEMM;
       op.name = name + "T";
       op.sg = {ws<float>(ctxn), dptr<float>(e, w.wq), ws<float>(T), C, C, C, (long long)C * C, 0, (long long)C * C};
-      op.bm = (C % 128 == 0 && C >= 384) ? 128 : 64;   // tile rows: keep >= ~128 CTAs in flight at B=8
+      op.bm = 64;
       op.grid = dim3(C / 64, C / op.bm, B);
     }
     raw_free(ctxn, cc_b);
@@ -778,7 +778,7 @@ struct Builder {
       op.kind = OP_SGEMM;
       op.name = name + "M";
       op.sg = {dptr<float>(e, w.woT), ws<float>(T), ws<float>(Mf), C, C, C, 0, (long long)C * C, (long long)C * C};
-      op.bm = (C % 128 == 0 && C >= 384) ? 128 : 64;
+      op.bm = 64;
       op.grid = dim3(C / 64, C / op.bm, B);
     }
     raw_free(T, cc_b);
@@ -1292,12 +1292,8 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
                  op.comb.nchunks, op.comb.out);
         break;
       case OP_SGEMM:
-        if (op.bm == 128)
-          launch_k(sgemm_tn_kernel<128>, op.grid, dim3(256), 0, st, op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N,
-                   op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC);
-        else
-          launch_k(sgemm_tn_kernel<64>, op.grid, dim3(256), 0, st, op.sg.At, op.sg.Bm, op.sg.Cout, op.sg.M, op.sg.N,
-                   op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC);
+        launch_k(gemm3xtf32_tn_kernel, op.grid, dim3(128), (size_t)Gemm3xSmem::kBytes, st, op.sg.At, op.sg.Bm,
+                 op.sg.Cout, op.sg.M, op.sg.N, op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC);
         break;
       case OP_LNROWS:
         launch_k(ln_rows_kernel, op.grid, dim3(256), 0, st, op.lnr);
@@ -1464,6 +1460,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_SLICE_SLOTS")) e->slice_slots = std::max(1, atoi(v));
   if (const char* v = getenv("CDC_SLICE_KMAX")) e->slice_kmax = std::max(1, atoi(v));
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
+  cudaFuncSetAttribute(gemm3xtf32_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3xSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   *out = e.release();
   return CDC_OK;
