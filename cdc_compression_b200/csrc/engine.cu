@@ -22,6 +22,7 @@
 #include "attn.cuh"
 #include "igemm_hmma.cuh"
 #include "igemm_tc.cuh"
+#include "attn_tc.cuh"
 #include "misc.cuh"
 
 using namespace cdc;
@@ -92,6 +93,8 @@ struct Op {
   dim3 grid{1, 1, 1};
   // attention
   AttnCtxParams actx{};
+  AttnTcParams atc{};      // tcgen05 form of the context kernel (use_tc; tensor maps in maps.a[0] / maps.b[0])
+  int atc_smem = 0;
   struct { const float *pc, *pm, *ps; int C, nchunks; float* out; } comb{};
   struct { const float *At, *Bm; float* Cout; int M, N, K; long long sA, sB, sC; } sg{};
   struct { const float *Mf, *g, *bln, *bout; int C; __half* Mg; float *um, *cm; } fin{};
@@ -203,6 +206,7 @@ struct cdc_engine {
   int num_sms = 148;
   int vreuse = 1;      // CDC_VREUSE: 0 off, 1 when it fits the default occupancy, 2 also at one CTA per SM
   bool sliced = true;  // CDC_SLICED=0 disables the sliced low-resolution mode (A/B measurements)
+  bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
   bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
   int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
   // derived structure
@@ -724,7 +728,12 @@ struct Builder {
     const int ntiles = (N + 63) / 64;
     // The split over pixels depends on (N, C) only — never on B — so every image goes through the same
     // sequence of fp32 additions whatever batch it is decoded in (batch-invariant, bit-reproducible shards).
-    const int tpc = std::max(8, (ntiles + 63) / 64);
+    // tcgen05 context kernel (attn_tc.cuh): C in {64, 128, 192}, whole 64-pixel tiles; ~18 pixel chunks per image and
+    // (K block, V block) pair keep 144 CTAs busy at the nominal batch of 8 and the partial buffers small.
+    const bool ctx_tc = e->mainloop == 1 && e->attn_tc && (C == 64 || C == 128 || C == 192) && N % 64 == 0;
+    const int pairs = C == 64 ? 1 : ((C + 127) / 128) * ((C + 127) / 128);
+    const int tpc = ctx_tc ? (ntiles + std::max(1, 18 / pairs) - 1) / std::max(1, 18 / pairs)
+                           : std::max(8, (ntiles + 63) / 64);
     const int nchunks = (ntiles + tpc - 1) / tpc;
     const size_t pc_b = (size_t)B * nchunks * C * C * 4, pv_b = (size_t)B * nchunks * C * 4;
     const size_t pc = raw_alloc(pc_b), pm = raw_alloc(pv_b), ps = raw_alloc(pv_b);
@@ -746,6 +755,21 @@ struct Builder {
       op.actx.part_m = ws<float>(pm);
       op.actx.part_s = ws<float>(ps);
       op.grid = dim3(nchunks, cb * cb, B);
+      if (ctx_tc) {
+        op.use_tc = true;
+        AttnTcParams& q = op.atc;
+        q.C = C; q.N = N;
+        q.stacked = C == 64;
+        q.cpt = cb;
+        q.kbc = (C + 127) / 128;
+        q.ntiles = ntiles;
+        q.tiles_per_chunk = tpc;
+        q.nchunks = nchunks;
+        q.stats = stats;
+        q.u = op.actx.u; q.c = op.actx.c;
+        q.part_ctx = op.actx.part_ctx; q.part_m = op.actx.part_m; q.part_s = op.actx.part_s;
+        op.grid = dim3(nchunks, pairs, B);
+      }
       // to_qkv 1x1 (3C x C per pixel) + the two einsums (2 * C*C per pixel) + to_out (C x C per pixel)
       op.flops = 2.0 * (double)B * N * C * (3.0 * C + 2.0 * C + C);
     }
@@ -1017,6 +1041,43 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   return 0;
 }
 
+// Tensor maps and pipeline depth of the tcgen05 attention-context kernel.
+int setup_attn_tc(cdc_engine* e, Plan* pl, Op& op) {
+  AttnTcParams& q = op.atc;
+  const int nblk = q.stacked ? 1 : 2;
+  const int fixed = 1024 + nblk * q.cpt * 16384 + 2 * nblk * 16384 + kAttnStatSlots * 512 + 512;
+  q.stages = std::max(2, std::min(8, (220 * 1024 - fixed) / 8192));
+  if (q.stacked) q.stages = std::min(q.stages, 4);   // leaves room for two CTAs per SM
+  op.atc_smem = attn_tc_smem_bytes(q.stacked, q.cpt, q.stages);
+  if (!pl->ws) return 0;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t C = (cuuint64_t)q.C;
+  {   // x: [B*N rows][C] fp16, box = 64 pixels x 64 channels
+    cuuint64_t gdim[2] = {C, (cuuint64_t)pl->B * q.N};
+    cuuint64_t gstr[1] = {C * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&op.maps.a[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)op.actx.x, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(attention x, op %s) failed: %d", op.name.c_str(), (int)r);
+  }
+  {   // Wkv [C/64][2C][64]: view {64, rows, kv, chunk}; stacked: rows = 2C (K then V) and one kv plane
+    const cuuint64_t rows = q.stacked ? 2 * C : C;
+    cuuint64_t gdim[4] = {64, rows, (cuuint64_t)(q.stacked ? 1 : 2), (cuuint64_t)q.cpt};
+    cuuint64_t gstr[3] = {128, C * 128, 2 * C * 128};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&op.maps.b[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)op.actx.Wkv, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(attention W, op %s) failed: %d", op.name.c_str(), (int)r);
+  }
+  for (int i = 1; i < kMaxSeg; ++i) { op.maps.a[i] = op.maps.a[0]; op.maps.b[i] = op.maps.b[0]; }
+  return 0;
+}
+
 int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
   const cdc_config& cfg = e->cfg;
   const int L = cfg.n_levels;
@@ -1170,6 +1231,10 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     std::vector<Op> ops2;
     ops2.reserve(pl->ops.size() + 64);
     for (auto& op : pl->ops) {
+      if (op.kind == OP_ATTN_CTX && op.use_tc) {
+        int rc = setup_attn_tc(e, pl, op);
+        if (rc) return rc;
+      }
       if (op.kind != OP_CONV) { ops2.push_back(op); continue; }
       int rc = setup_tc(e, pl, op);
       if (rc) return rc;
@@ -1285,7 +1350,10 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         break;
       }
       case OP_ATTN_CTX:
-        launch_k(attn_ctx_kernel, op.grid, dim3(256), (size_t)AttnCtxSmem::kBytes, st, op.actx);
+        if (op.use_tc)
+          launch_k(attn_ctx_tc_kernel, op.grid, dim3(kAttnTcThreads), (size_t)op.atc_smem, st, op.maps, op.atc);
+        else
+          launch_k(attn_ctx_kernel, op.grid, dim3(256), (size_t)AttnCtxSmem::kBytes, st, op.actx);
         break;
       case OP_COMBINE:
         launch_k(attn_combine_kernel, op.grid, dim3(128), 0, st, op.comb.pc, op.comb.pm, op.comb.ps, op.comb.C,
@@ -1454,12 +1522,14 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
   if (const char* v = getenv("CDC_NSLICE")) e->nslice = atoi(v) != 0;
+  if (const char* v = getenv("CDC_ATTN_TC")) e->attn_tc = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
   if (const char* v = getenv("CDC_PDL")) g_pdl = atoi(v) != 0;
   if (const char* v = getenv("CDC_SLICE_SLOTS")) e->slice_slots = std::max(1, atoi(v));
   if (const char* v = getenv("CDC_SLICE_KMAX")) e->slice_kmax = std::max(1, atoi(v));
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
+  cudaFuncSetAttribute(attn_ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(gemm3xtf32_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3xSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   *out = e.release();
