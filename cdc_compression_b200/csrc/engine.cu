@@ -730,10 +730,10 @@ struct Builder {
     // sequence of fp32 additions whatever batch it is decoded in (batch-invariant, bit-reproducible shards).
     // tcgen05 context kernel (attn_tc.cuh): C in {64, 128, 192}, whole 64-pixel tiles; ~18 pixel chunks per image and
     // (K block, V block) pair keep 144 CTAs busy at the nominal batch of 8 and the partial buffers small.
-    const bool ctx_tc = e->mainloop == 1 && e->attn_tc && (C == 64 || C == 128 || C == 192) && N % 64 == 0;
+    const bool ctx_tc = e->mainloop == 1 && e->attn_tc && (C == 64 || C == 128 || C == 192 || C == 256) && N % 64 == 0;
     const int pairs = C == 64 ? 1 : ((C + 127) / 128) * ((C + 127) / 128);
-    const int tpc = ctx_tc ? (ntiles + std::max(1, 18 / pairs) - 1) / std::max(1, 18 / pairs)
-                           : std::max(8, (ntiles + 63) / 64);
+    const int want_chunks = C == 64 ? 36 : std::max(1, 18 / pairs);   // C == 64 runs two CTAs per SM
+    const int tpc = ctx_tc ? (ntiles + want_chunks - 1) / want_chunks : std::max(8, (ntiles + 63) / 64);
     const int nchunks = (ntiles + tpc - 1) / tpc;
     const size_t pc_b = (size_t)B * nchunks * C * C * 4, pv_b = (size_t)B * nchunks * C * 4;
     const size_t pc = raw_alloc(pc_b), pm = raw_alloc(pv_b), ps = raw_alloc(pv_b);
