@@ -102,6 +102,7 @@ struct Op {
   bool use_tc = false;
   TcMaps maps;
   TcConvParams tcp{};
+  TcVecs64 vecs64{};       // C_out == 64 LayerNorm layers: bias / gain / offset passed by value
   int tc_grid = 0, tc_smem = 0, tc_occ = 1;
   // stream lane: 1 = runs on the engine's side stream concurrently with the main-lane ops that follow it (the 1x1
   // res_conv of a ResnetBlock overlaps block1); join_before = main lane must wait for the side lane first
@@ -543,7 +544,7 @@ cudaError_t launch_igemm(const Op& op, cudaStream_t st) {
   return cudaErrorInvalidValue;
 }
 
-template <int EPI, int OCC, bool N64>
+template <int EPI, int OCC, int N64>
 cudaError_t launch_tc_t(const Op& op, cudaStream_t st) {
   static bool attr_set[16] = {};
   int dev = 0;
@@ -555,20 +556,28 @@ cudaError_t launch_tc_t(const Op& op, cudaStream_t st) {
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
-  return launch_kc(igemm_tc_kernel<EPI, OCC, N64>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st,
-                   op.tcp.cluster_n, op.maps, op.tcp);
+  if constexpr (N64 == 2)
+    return launch_kc(igemm_tc_kernel<EPI, OCC, N64>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st,
+                     op.tcp.cluster_n, op.maps, op.tcp, op.vecs64);
+  else
+    return launch_kc(igemm_tc_kernel<EPI, OCC, N64>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st,
+                     op.tcp.cluster_n, op.maps, op.tcp, TcNoVecs{0});
 }
 
 cudaError_t launch_tc(const Op& op, cudaStream_t st) {
   const int occ = op.tc_occ;
   const bool ln = op.tcp.epi == EPI_LN_SHIFT || op.tcp.epi == EPI_LN_RES;
-  if (ln && op.tcp.Nc == 64) {
-    if (op.tcp.epi == EPI_LN_SHIFT) return launch_tc_t<EPI_LN_SHIFT, 2, true>(op, st);
-    return launch_tc_t<EPI_LN_RES, 2, true>(op, st);
+  if (ln && op.tcp.Nc == 64) {   // 64-column CTAs: row-in-registers LayerNorm epilogue
+    if (op.tcp.Ntot == 64) {     // C_out == 64: epilogue vectors travel as kernel parameters
+      if (op.tcp.epi == EPI_LN_SHIFT) return launch_tc_t<EPI_LN_SHIFT, 2, 2>(op, st);
+      return launch_tc_t<EPI_LN_RES, 2, 2>(op, st);
+    }
+    if (op.tcp.epi == EPI_LN_SHIFT) return launch_tc_t<EPI_LN_SHIFT, 2, 1>(op, st);
+    return launch_tc_t<EPI_LN_RES, 2, 1>(op, st);
   }
 #define CASE(E_)                                                \
   if (op.tcp.epi == E_) {                                       \
-    return occ == 2 ? launch_tc_t<E_, 2, false>(op, st) : launch_tc_t<E_, 1, false>(op, st); \
+    return occ == 2 ? launch_tc_t<E_, 2, 0>(op, st) : launch_tc_t<E_, 1, 0>(op, st); \
   }
   CASE(EPI_BIAS) CASE(EPI_LN_SHIFT) CASE(EPI_LN_RES) CASE(EPI_AFFINE) CASE(EPI_RAW)
 #undef CASE
@@ -1004,6 +1013,16 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   }
   op.tcp = t;
   op.use_tc = true;
+  if (ln_epi && N == 64) {   // host copies of the epilogue vectors (the blob's host image mirrors the device blob)
+    auto host_of = [&](const float* dev) {
+      return reinterpret_cast<const float*>(e->blob.host.data() + (reinterpret_cast<const uint8_t*>(dev) - e->dblob));
+    };
+    for (int i = 0; i < 64; ++i) {
+      op.vecs64.bias[i] = c.bias ? host_of(c.bias)[i] : 0.f;
+      op.vecs64.g[i] = c.ln_g ? host_of(c.ln_g)[i] : 1.f;
+      op.vecs64.b[i] = c.ln_b ? host_of(c.ln_b)[i] : 0.f;
+    }
+  }
   if (!pl->ws) return 0;  // dry run: geometry only
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");

@@ -18,6 +18,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "igemm_hmma.cuh"  // EpiKind
 
@@ -373,10 +375,21 @@ __device__ __forceinline__ void pack_out8(const float (&o)[8], uint4& hi, uint4&
 }
 
 // EPI: fused epilogue (compile-time, prunes the others); OCC: CTAs per SM the register budget is sized for.
-// N64: LayerNorm epilogue specialised for C_out == 64 (row held in registers, single TMEM pass).
-template <int EPI, int OCC, bool N64>
+// Per-channel epilogue vectors of a C_out == 64 layer passed BY VALUE (kernel parameters live in the constant bank: the
+// packed arithmetic reads them through uniform registers instead of shared-memory loads on the latency-bound path).
+struct TcVecs64 {
+  float bias[64], g[64], b[64];
+};
+struct TcNoVecs {
+  int unused;
+};
+
+// N64: LayerNorm epilogue specialised for 64-column CTAs (row held in registers, single TMEM pass).
+//   1 = epilogue vectors in shared memory (column slices of wider layers), 2 = vectors in the constant bank (C_out == 64).
+template <int EPI, int OCC, int N64>
 __global__ void __launch_bounds__(kTcThreads, OCC)
-igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
+igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
+                const __grid_constant__ typename std::conditional<N64 == 2, TcVecs64, TcNoVecs>::type kc) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -768,6 +781,25 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(s_vec);            // conv bias
         const ulonglong2* vg = reinterpret_cast<const ulonglong2*>(s_vec + vs);       // LayerNorm gain
         const ulonglong2* vo = reinterpret_cast<const ulonglong2*>(s_vec + 2 * vs);   // LayerNorm offset
+        // 4 consecutive entries (two packed pairs) of a per-channel vector: constant bank (N64 == 2) or shared memory
+        auto vec4 = [&](const ulonglong2* sm, const float* cst, int q4) -> ulonglong2 {
+          if constexpr (N64 == 2) {
+            (void)sm;
+            return make_ulonglong2(*reinterpret_cast<const unsigned long long*>(cst + 4 * q4),
+                                   *reinterpret_cast<const unsigned long long*>(cst + 4 * q4 + 2));
+          } else {
+            (void)cst;
+            return sm[q4];
+          }
+        };
+        const float* c_bias = nullptr;
+        const float* c_g = nullptr;
+        const float* c_b = nullptr;
+        if constexpr (N64 == 2) {
+          c_bias = kc.bias;
+          c_g = kc.g;
+          c_b = kc.b;
+        }
         const ulonglong2* shift2 =
             shift_smem ? reinterpret_cast<const ulonglong2*>(wvec)
                        : (EPI == EPI_LN_SHIFT && p.shift)
@@ -777,7 +809,8 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
         float mean, rstd;
         // finish 8 columns [c, c+8) of the row from their centred values d[0..3] (pairs) -> fp16 hi / lo pieces
         auto finish8 = [&](const f32x2 (&d)[4], int c, int j, uint4& hi, uint4& lo, f32x2 rstd2) {
-          const ulonglong2 g0 = vg[c >> 2], g1 = vg[(c >> 2) + 1], b0 = vo[c >> 2], b1 = vo[(c >> 2) + 1];
+          const ulonglong2 g0 = vec4(vg, c_g, c >> 2), g1 = vec4(vg, c_g, (c >> 2) + 1);
+          const ulonglong2 b0 = vec4(vo, c_b, c >> 2), b1 = vec4(vo, c_b, (c >> 2) + 1);
           f32x2 y[4];
           y[0] = tc::fma2(d[0], tc::mul2(rstd2, g0.x), b0.x);
           y[1] = tc::fma2(d[1], tc::mul2(rstd2, g0.y), b0.y);
@@ -820,7 +853,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p) {
           f32x2 s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const ulonglong2 ba = vb[i], bc = vb[8 + i];
+            const ulonglong2 ba = vec4(vb, c_bias, i), bc = vec4(vb, c_bias, 8 + i);
             x[2 * i] = tc::add2(tc::pku(v[4 * i], v[4 * i + 1]), ba.x);
             x[2 * i + 1] = tc::add2(tc::pku(v[4 * i + 2], v[4 * i + 3]), ba.y);
             x[16 + 2 * i] = tc::add2(tc::pku(v1[4 * i], v1[4 * i + 1]), bc.x);
