@@ -207,6 +207,9 @@ struct cdc_engine {
   int num_sms = 148;
   int vreuse = 1;      // CDC_VREUSE: 0 off, 1 when it fits the default occupancy, 2 also at one CTA per SM
   bool sliced = true;  // CDC_SLICED=0 disables the sliced low-resolution mode (A/B measurements)
+  bool final_kx = true; // final conv with the horizontal taps folded into N; CDC_FINAL_KX=0: 49-tap form
+  bool has_f_w2 = false;
+  size_t f_w2 = 0;
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
   bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
   int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
@@ -1407,7 +1410,12 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         fp.variant = cfg.variant;
         fp.pred_mode = a.pred;
         fp.clip_mode = a.clip;
-        launch_k(final_conv_kernel, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes, st, fp);
+        if (e->has_f_w2 && e->final_kx) {
+          fp.Wf = dptr<__half>(e, e->f_w2);
+          launch_k(final_conv_kx_kernel, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes2, st, fp);
+        } else {
+          launch_k(final_conv_kernel, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes, st, fp);
+        }
         break;
       }
       default:
@@ -1551,6 +1559,8 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   cudaFuncSetAttribute(attn_ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(gemm3xtf32_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3xSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
+  cudaFuncSetAttribute(final_conv_kx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes2);
+  if (const char* v = getenv("CDC_FINAL_KX")) e->final_kx = atoi(v) != 0;
   *out = e.release();
   return CDC_OK;
 }
@@ -1677,6 +1687,20 @@ int cdc_engine_finalize(cdc_engine* e) {
                 __float2half_rn(w->data[(((size_t)n * dim + c) * 7 + ky) * 7 + kx]);
     e->f_w = e->blob.reserve(wf.size() * 2);
     memcpy(e->blob.at<__half>(e->f_w), wf.data(), wf.size() * 2);
+    // channels <= 3: horizontal taps folded into N (final_conv_kx_kernel): row n = kx*channels + ch, k = ky*64 + c
+    e->f_w2 = 0;
+    if (cfg.channels <= 3) {
+      std::vector<__half> w2((size_t)24 * kFinalW2Stride, __float2half(0.f));
+      for (int n = 0; n < cfg.channels; ++n)
+        for (int c = 0; c < 64; ++c)
+          for (int ky = 0; ky < 7; ++ky)
+            for (int kx = 0; kx < 7; ++kx)
+              w2[(size_t)(kx * cfg.channels + n) * kFinalW2Stride + ky * 64 + c] =
+                  __float2half_rn(w->data[(((size_t)n * dim + c) * 7 + ky) * 7 + kx]);
+      e->f_w2 = e->blob.reserve(w2.size() * 2);
+      memcpy(e->blob.at<__half>(e->f_w2), w2.data(), w2.size() * 2);
+      e->has_f_w2 = true;
+    }
     e->f_bias = put_f32(e, b->data.data(), cfg.channels);
   }
   e->R = (int)bcat.size();

@@ -295,4 +295,193 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
       }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Same operator for channels <= 3 (every CDC configuration), restructured so that the tensor-core operand traffic no
+// longer dominates: with N = 3 output channels an MMA re-reads its whole A fragment for 3 useful columns, and the
+// 49-tap form above moves 2 MB of ldmatrix traffic per CTA (shared-memory bound, ~200 us at 8x256x256).  Here the
+// HORIZONTAL taps are moved into N:
+//     Y[y, hx, kx*nch + ch] = sum_{ky, c} LN(in)[y + ky - 3, hx, c] * w[ch, c, ky, kx]      (M = 16 x 22, N = 24, K = 448)
+//     out[y, x, ch]         = bias[ch] + sum_kx Y[y, x + kx, kx*nch + ch]                     (7 shifted adds per channel)
+// so K shrinks 7x and every A fragment feeds three n-tiles.  Halo pixel index = m + 22*ky for output-row-major m, i.e.
+// the vertical taps are plain row offsets into the same LayerNorm-ed halo tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFinalW2Stride = 7 * 64 + 8;     // halfs per weight row (k = ky*64 + c), padded: conflict-free ldmatrix
+constexpr int kFinalYStride = 26;              // floats per Y row (24 used)
+constexpr int kFinalSmemBytes2 = kFinalHalo * kFinalHalo * 128 + 24 * kFinalW2Stride * 2;
+
+__global__ void __launch_bounds__(256) final_conv_kx_kernel(const FinalParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sIn = smem;
+  float* sY = reinterpret_cast<float*>(smem);   // reuses the halo tile once the MMAs are done
+  __half* sW = reinterpret_cast<__half*>(smem + kFinalHalo * kFinalHalo * 128);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z, y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
+
+  pdl_launch_dependents();
+  {
+    const uint32_t dst = smem_u32(sW);
+    for (int i = tid; i < 24 * kFinalW2Stride * 2 / 16; i += 256)
+      cp_async16(dst + i * 16, reinterpret_cast<const uint4*>(p.Wf) + i, 16);
+    cp_async_commit();
+  }
+  pdl_wait();
+  // halo load + LayerNorm (as in final_conv_kernel): 8 threads per pixel, 8 channels each
+  {
+    const int j = tid & 7;
+    float g[8], bb[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      g[c] = p.ln_g[j * 8 + c];
+      bb[c] = p.ln_b[j * 8 + c];
+    }
+    constexpr int kBatch = 8;
+    for (int hp00 = 0; hp00 < kFinalHalo * kFinalHalo; hp00 += 32 * kBatch) {
+      uint4 raw[kBatch], rlo[kBatch];
+      bool inb[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int hp = hp00 + u * 32 + (tid >> 3);
+        const int hy = hp / kFinalHalo, hx = hp - hy * kFinalHalo;
+        const int yy = y0 + hy - 3, xx = x0 + hx - 3;
+        inb[u] = hp < kFinalHalo * kFinalHalo && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        rlo[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (inb[u]) {
+          const size_t off = (((size_t)b * p.H + yy) * p.W + xx) * 64 + j * 8;
+          raw[u] = *reinterpret_cast<const uint4*>(p.in + off);
+          if (p.in_lo) rlo[u] = *reinterpret_cast<const uint4*>(p.in_lo + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int hp = hp00 + u * 32 + (tid >> 3);
+        float v[8];
+        float2 f;
+        f = unpack_half2(raw[u].x); v[0] = f.x; v[1] = f.y;
+        f = unpack_half2(raw[u].y); v[2] = f.x; v[3] = f.y;
+        f = unpack_half2(raw[u].z); v[4] = f.x; v[5] = f.y;
+        f = unpack_half2(raw[u].w); v[6] = f.x; v[7] = f.y;
+        f = unpack_half2(rlo[u].x); v[0] += f.x; v[1] += f.y;
+        f = unpack_half2(rlo[u].y); v[2] += f.x; v[3] += f.y;
+        f = unpack_half2(rlo[u].z); v[4] += f.x; v[5] += f.y;
+        f = unpack_half2(rlo[u].w); v[6] += f.x; v[7] += f.y;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sum += v[c];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        const float mean = sum * (1.f / 64.f);
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float d = v[c] - mean;
+          q += d * d;
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 4);
+        const float rstd = 1.f / sqrtf(q * (1.f / 64.f) + 1e-5f);
+        if (hp < kFinalHalo * kFinalHalo) {
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (inb[u]) {
+            float y[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) y[c] = (v[c] - mean) * rstd * g[c] + bb[c];
+            o.x = pack_half2(y[0], y[1]);
+            o.y = pack_half2(y[2], y[3]);
+            o.z = pack_half2(y[4], y[5]);
+            o.w = pack_half2(y[6], y[7]);
+          }
+          *reinterpret_cast<uint4*>(sIn + swz128(hp, j)) = o;
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- Y = halo rows x (kx, ch): 22 m-tiles of 16 (output-row-major pixels incl. the horizontal halo), 3 n-tiles ----
+  float acc[3][3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][n][k] = 0.f;
+  const uint32_t sIn32 = smem_u32(sIn), sW32 = smem_u32(sW);
+  const int nmt = warp < 6 ? 3 : 2;   // m-tiles warp, warp + 8, warp + 16 (< 22)
+  for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks += 2) {
+      uint32_t bf[3][4];
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+        ldmatrix_x4(bf[nt], sW32 + ((nt * 8 + (lane & 7)) * kFinalW2Stride + ky * 64 + ks * 16 + (lane >> 3) * 8) * 2);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < nmt) {
+          const int hp = (warp + 8 * i) * 16 + (lane & 15) + kFinalHalo * ky;
+          uint32_t a0[4], a1[4];
+          ldmatrix_x4(a0, sIn32 + swz128(hp, ks * 2 + (lane >> 4)));
+          ldmatrix_x4(a1, sIn32 + swz128(hp, (ks + 1) * 2 + (lane >> 4)));
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) {
+            mma_16816(acc[i][nt], a0, bf[nt][0], bf[nt][1]);
+            mma_16816(acc[i][nt], a1, bf[nt][2], bf[nt][3]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();   // every warp is done with the halo tile: its memory becomes Y
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < nmt) {
+      const int m = (warp + 8 * i) * 16 + (lane >> 2);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const int n = nt * 8 + (lane & 3) * 2;
+        *reinterpret_cast<float2*>(sY + m * kFinalYStride + n) = make_float2(acc[i][nt][0], acc[i][nt][1]);
+        *reinterpret_cast<float2*>(sY + (m + 8) * kFinalYStride + n) = make_float2(acc[i][nt][2], acc[i][nt][3]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- horizontal taps + bias + sampler update: one output pixel per thread ----
+  const int ty = tid >> 4, tx = tid & 15;
+  const int yy = y0 + ty, xx = x0 + tx;
+  if (yy >= p.H || xx >= p.W) return;
+  const int nch = p.channels;
+  cdc_step_coef cf = {};
+  if (p.mode == 1) cf = p.table[*p.step_ptr];
+  const float* yrow = sY + (ty * kFinalHalo + tx) * kFinalYStride;
+  for (int n = 0; n < nch; ++n) {
+    float f = p.bias[n];
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) f += yrow[kx * kFinalYStride + kx * nch + n];
+    const size_t idx = (((size_t)b * nch + n) * p.H + yy) * p.W + xx;
+    if (p.mode == 0) {
+      p.out[idx] = f;
+      continue;
+    }
+    const float xt = p.x[idx];
+    float x0v, noise;
+    const bool clip = p.clip_mode == CDC_CLIP_FULL || (p.clip_mode == CDC_CLIP_HALF && b < p.B / 2);
+    if (p.variant == CDC_VARIANT_EPS || p.pred_mode == CDC_PRED_NOISE) {
+      x0v = cf.sqrt_recip_acp * xt - cf.sqrt_recipm1_acp * f;
+      if (clip) x0v = fminf(fmaxf(x0v, -1.f), 1.f);
+      noise = f;
+    } else {
+      x0v = (p.pred_mode == CDC_PRED_X) ? f : cf.sqrt_acp * xt - cf.sqrt_1m_acp * f;
+      if (clip) x0v = fminf(fmaxf(x0v, -1.f), 1.f);
+      noise = (cf.sqrt_recip_acp * xt - x0v) / cf.sqrt_recipm1_acp;
+    }
+    float xn = cf.sqrt_acp_prev * x0v + cf.dir_coef * noise;
+    if (p.z) xn += cf.noise_coef * p.z[idx];
+    p.x[idx] = xn;
+  }
+}
+
 }  // namespace cdc
