@@ -28,6 +28,7 @@ struct AttnCtxParams {
   float* part_ctx;      // [B][nchunks][C][C]
   float* part_m;        // [B][nchunks][C]
   float* part_s;        // [B][nchunks][C]
+  float* ctxn;          // nchunks == 1 only: write ctx / S straight to [B][C][C] (no combine pass); else nullptr
 };
 
 struct AttnCtxSmem {
@@ -290,19 +291,23 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
   // ---- write split partials ----
   {
     const int wd = warp >> 2, we = warp & 3;
-    float* dst = p.part_ctx + ((size_t)b * p.nchunks + chunk) * C * C;
+    const bool direct = p.ctxn != nullptr;   // single chunk: normalise here, the combine pass is skipped
+    float* dst = direct ? p.ctxn + (size_t)b * C * C : p.part_ctx + ((size_t)b * p.nchunks + chunk) * C * C;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int d = dblk * 64 + wd * 32 + mt * 16 + (lane >> 2) + h * 8;
+        const int dl = wd * 32 + mt * 16 + (lane >> 2) + h * 8;
+        const int d = dblk * 64 + dl;
+        const float inv = direct ? 1.f / s_run[dl] : 1.f;
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           const int e = eblk * 64 + we * 16 + nt * 8 + (lane & 3) * 2;
-          *reinterpret_cast<float2*>(dst + (size_t)d * C + e) = make_float2(ctx[mt][nt][2 * h], ctx[mt][nt][2 * h + 1]);
+          *reinterpret_cast<float2*>(dst + (size_t)d * C + e) =
+              make_float2(ctx[mt][nt][2 * h] * inv, ctx[mt][nt][2 * h + 1] * inv);
         }
       }
-    if (eblk == 0 && tid < 64) {
+    if (!direct && eblk == 0 && tid < 64) {
       const size_t o = ((size_t)b * p.nchunks + chunk) * C + dblk * 64 + tid;
       p.part_m[o] = m_run[(ntiles & 1) * 64 + tid];
       p.part_s[o] = s_run[tid];

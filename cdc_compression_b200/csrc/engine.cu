@@ -749,6 +749,9 @@ struct Builder {
     const int nchunks = (ntiles + tpc - 1) / tpc;
     const size_t pc_b = (size_t)B * nchunks * C * C * 4, pv_b = (size_t)B * nchunks * C * 4;
     const size_t pc = raw_alloc(pc_b), pm = raw_alloc(pv_b), ps = raw_alloc(pv_b);
+    const size_t cc_b = (size_t)B * C * C * 4;
+    const size_t ctxn = raw_alloc(cc_b);
+    const bool direct = !ctx_tc && nchunks == 1;   // mma.sync kernel, one chunk: it writes ctx / S itself
     {
       pl->ops.emplace_back();
       Op& op = pl->ops.back();
@@ -766,6 +769,7 @@ struct Builder {
       op.actx.part_ctx = ws<float>(pc);
       op.actx.part_m = ws<float>(pm);
       op.actx.part_s = ws<float>(ps);
+      op.actx.ctxn = direct ? ws<float>(ctxn) : nullptr;
       op.grid = dim3(nchunks, cb * cb, B);
       if (ctx_tc) {
         op.use_tc = true;
@@ -785,9 +789,7 @@ struct Builder {
       // to_qkv 1x1 (3C x C per pixel) + the two einsums (2 * C*C per pixel) + to_out (C x C per pixel)
       op.flops = 2.0 * (double)B * N * C * (3.0 * C + 2.0 * C + C);
     }
-    const size_t cc_b = (size_t)B * C * C * 4;
-    const size_t ctxn = raw_alloc(cc_b);
-    {
+    if (!direct) {
       pl->ops.emplace_back();
       Op& op = pl->ops.back();
       op.kind = OP_COMBINE;
@@ -924,14 +926,18 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   // summation order) must not depend on the batch size.
   const int tiles_nominal = ((h * w * 8 + 127) / 128) * (c.phases ? 4 : 1);
   t.Nc = N; t.n_slices = 1; t.k_splits = 1;
-  const bool sliceable = e->sliced && c.groups == 1 && op.epi != EPI_AFFINE && tiles_nominal < kSlicedMaxTiles && N >= 128;
+  // attention output GEMM (per-image weights, EPI_AFFINE): column slices only (no LayerNorm, no K split needed)
+  const bool affine_slices = e->sliced && e->nslice && op.epi == EPI_AFFINE && tiles_nominal < kSlicedMaxTiles && N >= 128;
+  const bool sliceable = affine_slices ||
+                         (e->sliced && c.groups == 1 && op.epi != EPI_AFFINE && tiles_nominal < kSlicedMaxTiles && N >= 128);
   // Fused column slices (default): no K split, the fused epilogue runs in the kernel; LayerNorm epilogues exchange
   // their row statistics inside a thread-block cluster of the n_slices CTAs of a tile (<= 8: portable cluster size).
   const bool ln_epi = op.epi == EPI_LN_SHIFT || op.epi == EPI_LN_RES;
   // Taken when the tile x slice grid alone gives enough CTAs (measured: >= 64 units, 128 for the 4-phase transposed
   // convolutions); the lowest levels keep the K-split + ln_rows_kernel form, and so do the stride-2 convolutions.
   const int units_nominal = tiles_nominal * (N / 64);
-  const bool fused = sliceable && e->nslice && N / 64 <= 8 && c.stride == 1 && units_nominal >= (c.phases ? 128 : 64);
+  const bool fused = affine_slices ||
+                     (sliceable && e->nslice && N / 64 <= 8 && c.stride == 1 && units_nominal >= (c.phases ? 128 : 64));
   t.cluster_n = 0;
   t.xchg_stats = 0;
   if (fused) {

@@ -686,8 +686,8 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
         if (img != cached_img) {                  // uniform across the warp
           if (EPI == EPI_AFFINE) {
             for (int i = lane * 4; i < N; i += 128) {
-              cp_async16(smem_u32(wvec + i), p.aff_u + (size_t)img * N + i, 16);
-              cp_async16(smem_u32(wvec + vs + i), p.aff_c + (size_t)img * N + i, 16);
+              cp_async16(smem_u32(wvec + i), p.aff_u + (size_t)img * p.Ntot + col0 + i, 16);
+              cp_async16(smem_u32(wvec + vs + i), p.aff_c + (size_t)img * p.Ntot + col0 + i, 16);
             }
           } else {
             for (int i = lane * 4; i < N; i += 128)
