@@ -8,7 +8,7 @@
 //
 // attn_ctx_kernel   : one pass over x per (image, pixel chunk, 64x64 block of ctx): K/V GEMM,
 //                     online softmax over pixels, P^T V accumulation; writes split partials.
-// attn_combine_kernel, gemm3xtf32_tn_kernel, attn_finish_kernel : per-image C x C algebra (fp32-grade, 3xTF32 MMAs).
+// attn_combine_kernel, gemm3xf16_tn_kernel, attn_finish_kernel : per-image C x C algebra (fp32-grade: split-fp16 MMAs).
 // The final GEMM (out = M_b-folded weights applied to raw x) runs in the generic conv kernel
 // with EPI_AFFINE and per-image weights.
 #pragma once
@@ -337,35 +337,30 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_ctx, const fl
   }
 }
 
-// Batched GEMM  Cout[b][m][n] = sum_k At[b][k][m] * Bm[b][k][n]   (M % 64 == 0, N % 64 == 0, K % 16 == 0) with fp32
-// inputs and outputs on the tensor cores: every operand is split into a TF32 "big" part and a TF32 remainder
-// (x = big + small, |small| <= 2^-11 |x|) and the product is accumulated as small*big + big*small + big*big in fp32
-// ("3xTF32": relative error ~1e-6, i.e. fp32-grade — single-pass TF32/fp16 here costs 1e-4 on the U-Net output).
+// Batched GEMM  Cout[b][m][n] = sum_k At[b][k][m] * Bm[b][k][n]   (M % 64 == 0, N % 64 == 0, K % 32 == 0) with fp32
+// inputs and outputs on the tensor cores: every operand is split into an fp16 value and its fp16 rounding remainder
+// (x = hi + lo, |lo| <= 2^-11 |x|) and the product is accumulated as lo*hi + hi*lo + hi*hi in fp32 (relative error
+// ~2^-21, i.e. fp32-grade — a single fp16 pass here costs 1e-4 on the U-Net output).  m16n8k16 fp16 MMAs: half the
+// instruction count of a 3xTF32 (m16n8k8) form (measured: 25 -> 19 us at C = 384; the legacy mma.sync rate bounds it).
 // These are the per-image C x C products behind M_b = W_out ctx^T (C^-1/2 W_q).
-// 64 x 64 tile per CTA, 4 warps of 32 x 32 (mma.sync m16n8k8), K slabs of 32 in a 3-stage cp.async ring (the K loop
-// is L2-latency bound: 12 slabs at C = 384).
-__device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& small) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(big) : "f"(x));
-  const float r = x - __uint_as_float(big);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(small) : "f"(r));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
+// 64 x 64 tile per CTA, 4 warps of 32 x 32, K slabs of 32 in a 3-stage cp.async ring.
 struct Gemm3xSmem {
-  static constexpr int kLD = 72;      // padded row (floats): fragment loads hit 32 distinct banks
+  static constexpr int kLD = 68;      // padded row (floats): the k-pair fragment loads hit 32 distinct banks
   static constexpr int kSlab = 32;    // K per pipeline stage (K % 32 == 0: C is a multiple of 64)
   static constexpr int kStages = 3;
   static constexpr int kBytes = 2 * kStages * kSlab * kLD * 4;
 };
 
-__global__ void __launch_bounds__(128) gemm3xtf32_tn_kernel(const float* __restrict__ At, const float* __restrict__ Bm,
-                                                            float* __restrict__ Cout, int M, int N, int K,
-                                                            long long sA, long long sB, long long sC) {
+// (x0, x1) -> packed fp16 pair hi and packed remainders lo
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_half2(x0, x1);
+  const float2 h = unpack_half2(hi);
+  lo = pack_half2(x0 - h.x, x1 - h.y);
+}
+
+__global__ void __launch_bounds__(128) gemm3xf16_tn_kernel(const float* __restrict__ At, const float* __restrict__ Bm,
+                                                           float* __restrict__ Cout, int M, int N, int K,
+                                                           long long sA, long long sB, long long sC) {
   constexpr int LD = Gemm3xSmem::kLD, KS = Gemm3xSmem::kSlab, ST = Gemm3xSmem::kStages;
   extern __shared__ __align__(16) uint8_t gsm[];
   float (*As)[KS][LD] = reinterpret_cast<float (*)[KS][LD]>(gsm);
@@ -409,28 +404,28 @@ __global__ void __launch_bounds__(128) gemm3xtf32_tn_kernel(const float* __restr
     if (sidx + ST - 1 < slabs) load((sidx + ST - 1) * KS, (sidx + ST - 1) % ST);
     cp_async_commit();
 #pragma unroll
-    for (int ks = 0; ks < KS / 8; ++ks) {
-      const int k0 = ks * 8;
-      uint32_t ab[2][4], as[2][4];
+    for (int ks = 0; ks < KS / 16; ++ks) {
+      const int k0 = ks * 16 + 2 * q;   // this lane's k pairs (k0, k0+1) and (k0+8, k0+9)
+      uint32_t ah[2][4], al[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const int m = wm + mt * 16 + g;
-        split_tf32(As[buf][k0 + q][m], ab[mt][0], as[mt][0]);
-        split_tf32(As[buf][k0 + q][m + 8], ab[mt][1], as[mt][1]);
-        split_tf32(As[buf][k0 + q + 4][m], ab[mt][2], as[mt][2]);
-        split_tf32(As[buf][k0 + q + 4][m + 8], ab[mt][3], as[mt][3]);
+        split_f16x2(As[buf][k0][m], As[buf][k0 + 1][m], ah[mt][0], al[mt][0]);
+        split_f16x2(As[buf][k0][m + 8], As[buf][k0 + 1][m + 8], ah[mt][1], al[mt][1]);
+        split_f16x2(As[buf][k0 + 8][m], As[buf][k0 + 9][m], ah[mt][2], al[mt][2]);
+        split_f16x2(As[buf][k0 + 8][m + 8], As[buf][k0 + 9][m + 8], ah[mt][3], al[mt][3]);
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int n = wn + nt * 8 + g;
-        uint32_t bb0, bs0, bb1, bs1;
-        split_tf32(Bs[buf][k0 + q][n], bb0, bs0);
-        split_tf32(Bs[buf][k0 + q + 4][n], bb1, bs1);
+        uint32_t bh0, bl0, bh1, bl1;
+        split_f16x2(Bs[buf][k0][n], Bs[buf][k0 + 1][n], bh0, bl0);
+        split_f16x2(Bs[buf][k0 + 8][n], Bs[buf][k0 + 9][n], bh1, bl1);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          mma_tf32(acc[mt][nt], as[mt], bb0, bb1);   // small terms first
-          mma_tf32(acc[mt][nt], ab[mt], bs0, bs1);
-          mma_tf32(acc[mt][nt], ab[mt], bb0, bb1);
+          mma_16816(acc[mt][nt], al[mt], bh0, bh1);   // small terms first
+          mma_16816(acc[mt][nt], ah[mt], bl0, bl1);
+          mma_16816(acc[mt][nt], ah[mt], bh0, bh1);
         }
       }
     }

@@ -1388,7 +1388,7 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
                  op.comb.nchunks, op.comb.out);
         break;
       case OP_SGEMM:
-        launch_k(gemm3xtf32_tn_kernel, op.grid, dim3(128), (size_t)Gemm3xSmem::kBytes, st, op.sg.At, op.sg.Bm,
+        launch_k(gemm3xf16_tn_kernel, op.grid, dim3(128), (size_t)Gemm3xSmem::kBytes, st, op.sg.At, op.sg.Bm,
                  op.sg.Cout, op.sg.M, op.sg.N, op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC);
         break;
       case OP_LNROWS:
@@ -1563,7 +1563,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_SLICE_KMAX")) e->slice_kmax = std::max(1, atoi(v));
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
   cudaFuncSetAttribute(attn_ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(gemm3xtf32_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3xSmem::kBytes);
+  cudaFuncSetAttribute(gemm3xf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3xSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   cudaFuncSetAttribute(final_conv_kx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes2);
   if (const char* v = getenv("CDC_FINAL_KX")) e->final_kx = atoi(v) != 0;
