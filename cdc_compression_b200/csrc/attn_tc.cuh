@@ -32,6 +32,7 @@ struct AttnTcParams {
   int ntiles;               // 64-pixel tiles per image
   int tiles_per_chunk, nchunks;
   int stages;               // X ring depth
+  int pvbufs;               // P/V tile buffers: 2, or 1 when the resident weights leave no room (C = 320)
   const float2* stats;      // [B*N] (mean, rstd) of the x rows
   const float* u;           // [2C] row sums of the folded fp16 weights
   const float* c;           // [2C] W b_ln
@@ -44,9 +45,9 @@ constexpr int kAttnTcThreads = 192;
 constexpr int kAttnStatSlots = 16;
 // dynamic smem: W tiles | X ring | P/V tiles (2 buffers) | statistics slots | barriers
 __host__ __device__ inline int attn_tc_nblk(int stacked) { return stacked ? 1 : 2; }
-__host__ __device__ inline int attn_tc_smem_bytes(int stacked, int cpt, int stages) {
+__host__ __device__ inline int attn_tc_smem_bytes(int stacked, int cpt, int stages, int pvbufs) {
   const int nblk = attn_tc_nblk(stacked);
-  return 1024 + nblk * cpt * 16384 + stages * 8192 + 2 * nblk * 16384 + kAttnStatSlots * 512 + 512;
+  return 1024 + nblk * cpt * 16384 + stages * 8192 + pvbufs * nblk * 16384 + kAttnStatSlots * 512 + 512;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -65,7 +66,7 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
   const uint32_t sW = base;                                   // [blk][cc] 16 KB tiles (128 rows x 64 ch)
   const uint32_t sX = sW + nblk * p.cpt * 16384;              // [stage] 8 KB tiles (64 px x 64 ch)
   const uint32_t sPV = sX + p.stages * 8192;                  // [buf][blk] 16 KB tiles (128 rows x 64 px)
-  const uint32_t sStat = sPV + 2 * nblk * 16384;              // [slot] negmean[64] | rstd[64]
+  const uint32_t sStat = sPV + p.pvbufs * nblk * 16384;       // [slot] negmean[64] | rstd[64]
   uint8_t* pPV = smem + (sPV - base);
   float* pStat = reinterpret_cast<float*>(smem + (sStat - base));
   const uint32_t bars = sStat + kAttnStatSlots * 512;
@@ -171,8 +172,9 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
     int stage = 0;
     uint32_t phase = 0;
     auto gemm2 = [&](int j) {
-      const int pb = j & 1;
-      tc::mbar_wait(bar_pvf + 8 * pb, (uint32_t)(j >> 1) & 1u);
+      const int pb = p.pvbufs == 2 ? (j & 1) : 0;
+      const int pu = p.pvbufs == 2 ? (j >> 1) : j;       // how often this buffer was used before
+      tc::mbar_wait(bar_pvf + 8 * pb, (uint32_t)pu & 1u);
       tc::tc_fence_after();
       if (leader) {
         const uint32_t a_lo = (uint32_t)tc::make_desc_sw128(sPV + (pb * nblk) * 16384);
@@ -237,7 +239,9 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
       const int buf = i & 1;
       const ulonglong2* nm = reinterpret_cast<const ulonglong2*>(pStat + (i % kAttnStatSlots) * 128);   // -mean pairs
       const ulonglong2* rs = nm + 16;                                                                 // rstd pairs
-      tc::mbar_wait(bar_pve + 8 * buf, ((uint32_t)(i >> 1) & 1u) ^ 1u);   // GEMM2 of tile i-2 released this P/V buffer
+      const int pb = p.pvbufs == 2 ? buf : 0;
+      const int pu = p.pvbufs == 2 ? (i >> 1) : i;
+      tc::mbar_wait(bar_pve + 8 * pb, ((uint32_t)pu & 1u) ^ 1u);   // the previous GEMM2 on this P/V buffer has retired
       tc::mbar_wait(bar_st + 8 * (i % kAttnStatSlots), (uint32_t)(i / kAttnStatSlots) & 1u);
       tc::mbar_wait(bar_d1f + 8 * buf, (uint32_t)(i >> 1) & 1u);
       tc::tc_fence_after();
@@ -251,7 +255,7 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
           tc::mbar_arrive(bar_d1e + 8 * buf);
         }
         const bool is_k = blk == 0 && row0_is_k;   // uniform per warp
-        uint8_t* dst = pPV + (size_t)(buf * nblk + blk) * 16384 + r * 128;
+        uint8_t* dst = pPV + (size_t)(pb * nblk + blk) * 16384 + r * 128;
         f32x2 x[32];
         if (is_k) {
           float tmax = -INFINITY;
@@ -268,7 +272,8 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
           const bool raise = m_new != m_ref && i > 0;
           if (__any_sync(0xffffffffu, raise)) {
             const float alpha = raise ? __expf(m_ref - m_new) : 1.f;
-            tc::mbar_wait(bar_pve + 8 * ((i - 1) & 1), (uint32_t)((i - 1) >> 1) & 1u);   // GEMM2 of tile i-1 retired
+            if (p.pvbufs == 2)   // GEMM2 of tile i-1 retired (with one buffer the wait above already covers it)
+              tc::mbar_wait(bar_pve + 8 * ((i - 1) & 1), (uint32_t)((i - 1) >> 1) & 1u);
             tc::tc_fence_after();
             for (int c0 = 0; c0 < n2; c0 += 32) {
               uint32_t t[32];
@@ -323,7 +328,7 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
       }
       tc::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc::tc_fence_before();
-      tc::mbar_arrive(bar_pvf + 8 * buf);
+      tc::mbar_arrive(bar_pvf + 8 * pb);
     }
 
     // ---- write the split partials: ctx rows of this CTA's K block x V block, reference maximum, sum ----

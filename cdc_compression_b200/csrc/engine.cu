@@ -742,7 +742,7 @@ struct Builder {
     // sequence of fp32 additions whatever batch it is decoded in (batch-invariant, bit-reproducible shards).
     // tcgen05 context kernel (attn_tc.cuh): C in {64, 128, 192}, whole 64-pixel tiles; ~18 pixel chunks per image and
     // (K block, V block) pair keep 144 CTAs busy at the nominal batch of 8 and the partial buffers small.
-    const bool ctx_tc = e->mainloop == 1 && e->attn_tc && (C == 64 || C == 128 || C == 192 || C == 256) && N % 64 == 0;
+    const bool ctx_tc = e->mainloop == 1 && e->attn_tc && (C == 64 || C == 128 || C == 192 || C == 256 || C == 320) && N % 64 == 0;
     const int pairs = C == 64 ? 1 : ((C + 127) / 128) * ((C + 127) / 128);
     const int want_chunks = C == 64 ? 36 : std::max(1, 18 / pairs);   // C == 64 runs two CTAs per SM
     const int tpc = ctx_tc ? (ntiles + want_chunks - 1) / want_chunks : std::max(8, (ntiles + 63) / 64);
@@ -1073,10 +1073,11 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
 int setup_attn_tc(cdc_engine* e, Plan* pl, Op& op) {
   AttnTcParams& q = op.atc;
   const int nblk = q.stacked ? 1 : 2;
-  const int fixed = 1024 + nblk * q.cpt * 16384 + 2 * nblk * 16384 + kAttnStatSlots * 512 + 512;
-  q.stages = std::max(2, std::min(8, (220 * 1024 - fixed) / 8192));
+  q.pvbufs = q.C > 256 ? 1 : 2;   // C = 320: 160 KB of resident weights
+  const int fixed = 1024 + nblk * q.cpt * 16384 + q.pvbufs * nblk * 16384 + kAttnStatSlots * 512 + 512;
+  q.stages = std::max(2, std::min(8, (224 * 1024 - fixed) / 8192));
   if (q.stacked) q.stages = std::min(q.stages, 4);   // leaves room for two CTAs per SM
-  op.atc_smem = attn_tc_smem_bytes(q.stacked, q.cpt, q.stages);
+  op.atc_smem = attn_tc_smem_bytes(q.stacked, q.cpt, q.stages, q.pvbufs);
   if (!pl->ws) return 0;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
