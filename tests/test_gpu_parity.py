@@ -329,3 +329,45 @@ def test_large_shape_512_runs_and_is_finite():
     y1 = d.denoise_fn(x[:1].to(dev()), t[:1].to(dev()), [c[:1].to(dev()) for c in ctx])
     assert torch.isfinite(y2).all()
     assert torch.equal(y2[:1], y1)
+
+
+KERNEL_FORMS = [("CDC_ATTN_TC", "mma.sync attention-context kernel instead of the tcgen05 one"),
+                ("CDC_NSLICE", "K-split partial tiles + ln_rows_kernel instead of fused column slices / cluster LayerNorm"),
+                ("CDC_FINAL_KX", "49-tap final convolution instead of the horizontal-taps-in-N form"),
+                ("CDC_SLICED", "whole-row tiles at every level")]
+
+
+@pytest.mark.parametrize("knob", [k for k, _ in KERNEL_FORMS])
+def test_alternative_kernel_forms_agree(knob):
+    """Every optimised kernel form has a simpler sibling selected by an environment knob (read when an engine is
+    created).  Both forms implement the same rounding points; their outputs differ by fp32 summation order (and, for
+    the attention kernel, by the softmax reference maximum) — inside the oracle tolerance.
+    128x128 / B=2 reaches: cluster LayerNorm at levels 1-3, the legacy sliced form below, attention tc kernel at
+    C = 64..320, single-chunk context normalisation at C = 384."""
+    from cdc_compression_b200 import DenoiserEngine
+    variant, B, H, W, seed = "eps", 2, 128, 128, 3
+    sd = O.seeded_unet_state_dict(variant, seed)
+    x, t, ctx, _ = case_inputs(variant, B, H, W, seed)
+    xd, td, ctxd = x.to(dev()), t.reshape(-1).to(dev()), [c.to(dev()) for c in ctx]
+    outs = {}
+    old = os.environ.get(knob)
+    try:
+        for val in ("1", "0"):
+            os.environ[knob] = val
+            eng = DenoiserEngine(variant, 64, (1, 2, 3, 4, 5, 6), (1, 2, 3, 4), 3, 3, dev())
+            eng.load_weights(sd)
+            outs[val] = eng.forward(xd, td, ctxd).cpu()
+            del eng
+    finally:
+        if old is None:
+            os.environ.pop(knob, None)
+        else:
+            os.environ[knob] = old
+    sd64 = {k: v.double() for k, v in sd.items()}
+    y64 = O.unet_forward(sd64, x.double(), t.double(), [c.double() for c in ctx])
+    assert rel(outs["1"], y64) < REL_L2_UNET and rel(outs["0"], y64) < REL_L2_UNET
+    # A different fp32 summation order flips a few fp16 roundings early in the network and the difference grows to
+    # the size of the rounding noise itself (measured 4.0e-4 .. 4.8e-4 between forms, each 6e-4 from the oracle):
+    # the forms are two draws of the same noise, so they must agree to within the oracle tolerance, not better.
+    tol = 8e-4
+    assert rel(outs["1"], outs["0"]) < tol, rel(outs["1"], outs["0"])
