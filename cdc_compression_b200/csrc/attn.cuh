@@ -358,9 +358,23 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   lo = pack_half2(x0 - h.x, x1 - h.y);
 }
 
+// Optional fused "finish" epilogue of the second product (M_b = W_out T): instead of the fp32 matrix the kernel writes
+//   Mg16[o][c] = half(M[o][c] * g[c])   in the conv kernel's per-image weight layout [C/64][C][64], and per 64-column
+//   tile t the partial row sums  um_part[b][t][o] = sum_c float(Mg16[o][c]),  cm_part[b][t][o] = sum_c M[o][c] b_ln[c]
+//   (+ b_out[o] in tile 0); the consumer (EPI_AFFINE epilogue of igemm_tc_kernel) adds the C/64 partials in tile order.
+struct GemmFinish {
+  const float* g;      // [C] LayerNorm gain; nullptr = plain fp32 output
+  const float* bln;    // [C]
+  const float* bout;   // [C]
+  __half* Mg16;        // [B][C/64][C][64]
+  float* um_part;      // [B][C/64][C]
+  float* cm_part;
+};
+
 __global__ void __launch_bounds__(128) gemm3xf16_tn_kernel(const float* __restrict__ At, const float* __restrict__ Bm,
                                                            float* __restrict__ Cout, int M, int N, int K,
-                                                           long long sA, long long sB, long long sC) {
+                                                           long long sA, long long sB, long long sC,
+                                                           const GemmFinish fin) {
   constexpr int LD = Gemm3xSmem::kLD, KS = Gemm3xSmem::kSlab, ST = Gemm3xSmem::kStages;
   extern __shared__ __align__(16) uint8_t gsm[];
   float (*As)[KS][LD] = reinterpret_cast<float (*)[KS][LD]>(gsm);
@@ -430,14 +444,54 @@ __global__ void __launch_bounds__(128) gemm3xf16_tn_kernel(const float* __restri
       }
     }
   }
+  if (fin.g == nullptr) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int m = m0 + wm + mt * 16 + g, n = n0 + wn + nt * 8 + q * 2;
+        *reinterpret_cast<float2*>(Cout + (size_t)m * N + n) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<float2*>(Cout + (size_t)(m + 8) * N + n) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      }
+    return;
+  }
+  // ---- fused finish (M == N == C, this CTA = rows [m0, +64) x column tile blockIdx.x) ----
+  __syncthreads();                                   // the pipeline buffers are free: reuse them for the row sums
+  float* red = reinterpret_cast<float*>(gsm);        // [2 (u|c)][2 (wn half)][64 rows]
+  const int ct = blockIdx.x;
+  __half* mg = fin.Mg16 + (size_t)b * M * N + (size_t)ct * M * 64;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int m = m0 + wm + mt * 16 + g, n = n0 + wn + nt * 8 + q * 2;
-      *reinterpret_cast<float2*>(Cout + (size_t)m * N + n) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-      *reinterpret_cast<float2*>(Cout + (size_t)(m + 8) * N + n) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    for (int h = 0; h < 2; ++h) {
+      const int ml = wm + mt * 16 + g + h * 8;       // row inside the tile
+      float su = 0.f, sc = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int nl = wn + nt * 8 + q * 2, n = n0 + nl;
+        const float v0 = acc[mt][nt][2 * h], v1 = acc[mt][nt][2 * h + 1];
+        const uint32_t hv = pack_half2(v0 * fin.g[n], v1 * fin.g[n + 1]);
+        *reinterpret_cast<uint32_t*>(mg + (size_t)(m0 + ml) * 64 + nl) = hv;
+        const float2 f = unpack_half2(hv);
+        su += f.x + f.y;
+        sc += v0 * fin.bln[n] + v1 * fin.bln[n + 1];
+      }
+      su += __shfl_xor_sync(0xffffffffu, su, 1);
+      su += __shfl_xor_sync(0xffffffffu, su, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      if (q == 0) {
+        red[(0 * 2 + (warp & 1)) * 64 + ml] = su;
+        red[(1 * 2 + (warp & 1)) * 64 + ml] = sc;
+      }
     }
+  __syncthreads();
+  if (tid < 64) {
+    const int m = m0 + tid;
+    const size_t o = ((size_t)b * (N >> 6) + ct) * M + m;
+    fin.um_part[o] = red[tid] + red[64 + tid];
+    fin.cm_part[o] = red[128 + tid] + red[192 + tid] + (ct == 0 ? fin.bout[m] : 0.f);
+  }
 }
 
 // Per (image, output row o): Mg16 = half(M[o][:] * g), um = rowsum(float(Mg16)), cm = M[o][:].b_ln + b_out[o].

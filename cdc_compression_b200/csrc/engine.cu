@@ -97,6 +97,7 @@ struct Op {
   int atc_smem = 0;
   struct { const float *pc, *pm, *ps; int C, nchunks; float* out; } comb{};
   struct { const float *At, *Bm; float* Cout; int M, N, K; long long sA, sB, sC; } sg{};
+  GemmFinish gfin{};       // OP_SGEMM: fused finish epilogue (second attention product)
   struct { const float *Mf, *g, *bln, *bout; int C; __half* Mg; float *um, *cm; } fin{};
   // tcgen05 path (stride-1 convolutions when the engine's mainloop is 1)
   bool use_tc = false;
@@ -210,6 +211,7 @@ struct cdc_engine {
   bool final_kx = true; // final conv with the horizontal taps folded into N; CDC_FINAL_KX=0: 49-tap form
   bool has_f_w2 = false;
   size_t f_w2 = 0;
+  bool fold_finish = true;   // attn_finish_kernel fused into the second C x C product; CDC_FOLD_FINISH=0: separate kernel
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
   bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
   int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
@@ -809,7 +811,13 @@ struct Builder {
       op.grid = dim3(C / 64, C / op.bm, B);
     }
     raw_free(ctxn, cc_b);
+    // tcgen05 path: the second product writes M_b in fp16 weight layout and per-column-tile partial row sums itself
+    // (fused finish); the mma.sync convolution keeps the separate finish kernel and whole-row sums.
+    const bool fold = e->mainloop == 1 && e->fold_finish;
+    const int parts = fold ? cb : 1;
     const size_t Mf = raw_alloc(cc_b);
+    const size_t mg_b = (size_t)B * C * C * 2, v_b = (size_t)B * parts * C * 4;
+    const size_t Mg = raw_alloc(mg_b), um = raw_alloc(v_b), cm = raw_alloc(v_b);
     {
       pl->ops.emplace_back();
       Op& op = pl->ops.back();
@@ -818,11 +826,12 @@ struct Builder {
       op.sg = {dptr<float>(e, w.woT), ws<float>(T), ws<float>(Mf), C, C, C, 0, (long long)C * C, (long long)C * C};
       op.bm = 64;
       op.grid = dim3(C / 64, C / op.bm, B);
+      if (fold)
+        op.gfin = {dptr<float>(e, w.g), dptr<float>(e, w.bln), dptr<float>(e, w.bout), ws<__half>(Mg), ws<float>(um),
+                   ws<float>(cm)};
     }
     raw_free(T, cc_b);
-    const size_t mg_b = (size_t)B * C * C * 2, v_b = (size_t)B * C * 4;
-    const size_t Mg = raw_alloc(mg_b), um = raw_alloc(v_b), cm = raw_alloc(v_b);
-    {
+    if (!fold) {
       pl->ops.emplace_back();
       Op& op = pl->ops.back();
       op.kind = OP_FINISH;
@@ -847,6 +856,7 @@ struct Builder {
       p.aff_u = ws<float>(um);
       p.aff_c = ws<float>(cm);
       p.aff_group_stride = C;
+      p.aff_parts = parts;
       p.res = ws<__half>(x.off);
       p.res_lo = lo_ptr<__half>(x);
       p.res_C0 = C;
@@ -1007,6 +1017,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.bias = c.bias; t.ln_g = c.ln_g; t.ln_b = c.ln_b; t.shift = c.shift; t.shift_stride = c.shift_stride;
   t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2; t.res_lo = c.res_lo; t.res2_lo = c.res2_lo;
   t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
+  t.aff_parts = c.aff_parts;
   op.tc_smem = tc_smem_bytes(stage_bytes, t.stages, Nc, t.cluster_n, xsets);
   op.tc_occ = ctas_per_sm;
   op.tc_grid = std::min(tiles_total * t.n_slices * t.k_splits, e->num_sms * ctas_per_sm);
@@ -1390,7 +1401,7 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         break;
       case OP_SGEMM:
         launch_k(gemm3xf16_tn_kernel, op.grid, dim3(128), (size_t)Gemm3xSmem::kBytes, st, op.sg.At, op.sg.Bm,
-                 op.sg.Cout, op.sg.M, op.sg.N, op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC);
+                 op.sg.Cout, op.sg.M, op.sg.N, op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC, op.gfin);
         break;
       case OP_LNROWS:
         launch_k(ln_rows_kernel, op.grid, dim3(256), 0, st, op.lnr);
@@ -1557,6 +1568,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
   if (const char* v = getenv("CDC_NSLICE")) e->nslice = atoi(v) != 0;
   if (const char* v = getenv("CDC_ATTN_TC")) e->attn_tc = atoi(v) != 0;
+  if (const char* v = getenv("CDC_FOLD_FINISH")) e->fold_finish = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
   if (const char* v = getenv("CDC_PDL")) g_pdl = atoi(v) != 0;

@@ -68,8 +68,9 @@ struct TcConvParams {
   const __half* res_lo;
   const __half* res2_lo;
   const float2* stats_in;
-  const float* aff_u;        // [B][Ntot] (per image)
+  const float* aff_u;        // [B][aff_parts][Ntot] (per image): partial sums, added in order by the epilogue
   const float* aff_c;
+  int aff_parts;
   float2* stats_out;
   // Sliced mode (low-resolution layers: few output tiles, long K, wide N).  The work of one output tile is spread
   // over n_slices x k_splits CTAs: each computes columns [slice*Nc, +Nc) over a K sub-range and stores its fp32
@@ -685,9 +686,24 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
         const int img = min(tb * p.TB, p.B - 1);  // TB == 1: one image per tile
         if (img != cached_img) {                  // uniform across the warp
           if (EPI == EPI_AFFINE) {
-            for (int i = lane * 4; i < N; i += 128) {
-              cp_async16(smem_u32(wvec + i), p.aff_u + (size_t)img * p.Ntot + col0 + i, 16);
-              cp_async16(smem_u32(wvec + vs + i), p.aff_c + (size_t)img * p.Ntot + col0 + i, 16);
+            if (p.aff_parts <= 1) {
+              for (int i = lane * 4; i < N; i += 128) {
+                cp_async16(smem_u32(wvec + i), p.aff_u + (size_t)img * p.Ntot + col0 + i, 16);
+                cp_async16(smem_u32(wvec + vs + i), p.aff_c + (size_t)img * p.Ntot + col0 + i, 16);
+              }
+            } else {   // per-column-tile partial sums (fused finish of the M_b product): add them in tile order
+              for (int i = lane * 4; i < N; i += 128) {
+                float4 su = make_float4(0.f, 0.f, 0.f, 0.f), sc = su;
+                for (int t2 = 0; t2 < p.aff_parts; ++t2) {
+                  const size_t o = ((size_t)img * p.aff_parts + t2) * p.Ntot + col0 + i;
+                  const float4 a = *reinterpret_cast<const float4*>(p.aff_u + o);
+                  const float4 c4 = *reinterpret_cast<const float4*>(p.aff_c + o);
+                  su.x += a.x; su.y += a.y; su.z += a.z; su.w += a.w;
+                  sc.x += c4.x; sc.y += c4.y; sc.z += c4.z; sc.w += c4.w;
+                }
+                *reinterpret_cast<float4*>(wvec + i) = su;
+                *reinterpret_cast<float4*>(wvec + vs + i) = sc;
+              }
             }
           } else {
             for (int i = lane * 4; i < N; i += 128)
