@@ -39,6 +39,7 @@ struct AttnTcParams {
   float* part_ctx;          // [B][nchunks][C][C]
   float* part_m;            // [B][nchunks][C]
   float* part_s;            // [B][nchunks][C]
+  float* ctxn;              // nchunks == 1 only: write ctx / S straight to [B][C][C] (no combine pass); else nullptr
 };
 
 constexpr int kAttnTcThreads = 192;
@@ -336,7 +337,10 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
     tc::tc_fence_after();
     if (row0_is_k) {   // uniform per warp
       const size_t pbase = (size_t)b * p.nchunks + chunk;
-      float* dst = p.part_ctx + (pbase * p.C + (k_ok ? gk : 0)) * p.C + vb * 128;
+      const bool direct = p.ctxn != nullptr;   // single chunk: normalise here, the combine pass is skipped
+      float* dst = (direct ? p.ctxn + ((size_t)b * p.C + (k_ok ? gk : 0)) * p.C
+                           : p.part_ctx + (pbase * p.C + (k_ok ? gk : 0)) * p.C) + vb * 128;
+      const float inv = direct ? 1.f / S : 1.f;
       const int ncol = min(n2, p.C - vb * 128);
       for (int c0 = 0; c0 < ncol; c0 += 32) {
         uint32_t t[32];
@@ -344,10 +348,12 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
         if (k_ok) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            reinterpret_cast<uint4*>(dst + c0)[q] = make_uint4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+            reinterpret_cast<float4*>(dst + c0)[q] =
+                make_float4(__uint_as_float(t[4 * q]) * inv, __uint_as_float(t[4 * q + 1]) * inv,
+                            __uint_as_float(t[4 * q + 2]) * inv, __uint_as_float(t[4 * q + 3]) * inv);
         }
       }
-      if (k_ok && vb == 0) {
+      if (!direct && k_ok && vb == 0) {
         p.part_m[pbase * p.C + gk] = m_ref;
         p.part_s[pbase * p.C + gk] = S;
       }

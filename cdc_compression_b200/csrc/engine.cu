@@ -753,7 +753,7 @@ struct Builder {
     const size_t pc = raw_alloc(pc_b), pm = raw_alloc(pv_b), ps = raw_alloc(pv_b);
     const size_t cc_b = (size_t)B * C * C * 4;
     const size_t ctxn = raw_alloc(cc_b);
-    const bool direct = !ctx_tc && nchunks == 1;   // mma.sync kernel, one chunk: it writes ctx / S itself
+    const bool direct = nchunks == 1;   // one pixel chunk: the context kernel writes ctx / S itself
     {
       pl->ops.emplace_back();
       Op& op = pl->ops.back();
@@ -786,6 +786,7 @@ struct Builder {
         q.stats = stats;
         q.u = op.actx.u; q.c = op.actx.c;
         q.part_ctx = op.actx.part_ctx; q.part_m = op.actx.part_m; q.part_s = op.actx.part_s;
+        q.ctxn = op.actx.ctxn;
         op.grid = dim3(nchunks, pairs, B);
       }
       // to_qkv 1x1 (3C x C per pixel) + the two einsums (2 * C*C per pixel) + to_out (C x C per pixel)
