@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["csrc/engine.cu"]
-HEADERS = ["csrc/common.cuh", "csrc/igemm_hmma.cuh", "csrc/igemm_tc.cuh", "csrc/attn.cuh", "csrc/attn_tc.cuh", "csrc/misc.cuh", "../include/cdc_b200.h"]
+HEADERS = ["csrc/common.cuh", "csrc/igemm_hmma.cuh", "csrc/igemm_tc.cuh", "csrc/attn.cuh", "csrc/attn_tc.cuh", "csrc/final_tc.cuh", "csrc/misc.cuh", "../include/cdc_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -24,6 +24,7 @@
 #include "igemm_tc.cuh"
 #include "attn_tc.cuh"
 #include "misc.cuh"
+#include "final_tc.cuh"
 
 using namespace cdc;
 
@@ -210,7 +211,8 @@ struct cdc_engine {
   bool sliced = true;  // CDC_SLICED=0 disables the sliced low-resolution mode (A/B measurements)
   bool final_kx = true; // final conv with the horizontal taps folded into N; CDC_FINAL_KX=0: 49-tap form
   bool has_f_w2 = false;
-  size_t f_w2 = 0;
+  size_t f_w2 = 0, f_w3 = 0;
+  bool final_tc = true; // tcgen05 form of the final conv (final_tc.cuh); CDC_FINAL_TC=0: mma.sync form
   bool fold_finish = true;   // attn_finish_kernel fused into the second C x C product; CDC_FOLD_FINISH=0: separate kernel
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
   bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
@@ -1429,7 +1431,10 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         fp.variant = cfg.variant;
         fp.pred_mode = a.pred;
         fp.clip_mode = a.clip;
-        if (e->has_f_w2 && e->final_kx) {
+        if (e->has_f_w2 && e->final_tc && e->mainloop == 1) {
+          fp.Wf = dptr<__half>(e, e->f_w3);
+          launch_k(final_conv_tc_kernel, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes3, st, fp);
+        } else if (e->has_f_w2 && e->final_kx) {
           fp.Wf = dptr<__half>(e, e->f_w2);
           launch_k(final_conv_kx_kernel, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes2, st, fp);
         } else {
@@ -1580,6 +1585,8 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   cudaFuncSetAttribute(gemm3xf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3xSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   cudaFuncSetAttribute(final_conv_kx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes2);
+  cudaFuncSetAttribute(final_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes3);
+  if (const char* v = getenv("CDC_FINAL_TC")) e->final_tc = atoi(v) != 0;
   if (const char* v = getenv("CDC_FINAL_KX")) e->final_kx = atoi(v) != 0;
   *out = e.release();
   return CDC_OK;
@@ -1720,6 +1727,18 @@ int cdc_engine_finalize(cdc_engine* e) {
       e->f_w2 = e->blob.reserve(w2.size() * 2);
       memcpy(e->blob.at<__half>(e->f_w2), w2.data(), w2.size() * 2);
       e->has_f_w2 = true;
+      // tcgen05 form (final_conv_tc_kernel): [ky][32 rows n][64 c], stored as the SWIZZLE_128B shared-memory image
+      std::vector<__half> w3((size_t)kFinalW3Bytes / 2, __float2half(0.f));
+      for (int n = 0; n < cfg.channels; ++n)
+        for (int c = 0; c < 64; ++c)
+          for (int ky = 0; ky < 7; ++ky)
+            for (int kx = 0; kx < 7; ++kx) {
+              const int row = kx * cfg.channels + n;
+              const size_t byte = (size_t)ky * 4096 + (size_t)row * 128 + ((((c >> 3) ^ (row & 7)) << 4)) + (c & 7) * 2;
+              w3[byte / 2] = __float2half_rn(w->data[(((size_t)n * dim + c) * 7 + ky) * 7 + kx]);
+            }
+      e->f_w3 = e->blob.reserve(w3.size() * 2);
+      memcpy(e->blob.at<__half>(e->f_w3), w3.data(), w3.size() * 2);
     }
     e->f_bias = put_f32(e, b->data.data(), cfg.channels);
   }
