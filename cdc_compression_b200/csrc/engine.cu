@@ -212,6 +212,7 @@ struct cdc_engine {
   bool final_kx = true; // final conv with the horizontal taps folded into N; CDC_FINAL_KX=0: 49-tap form
   bool has_f_w2 = false;
   size_t f_w2 = 0, f_w3 = 0;
+  bool final_preln = true;  // last Upsample writes the LayerNorm-ed fp16 input of the final conv; CDC_FINAL_PRELN=0: final conv normalises
   bool final_tc = true; // tcgen05 form of the final conv (final_tc.cuh); CDC_FINAL_TC=0: mma.sync form
   bool fold_finish = true;   // attn_finish_kernel fused into the second C x C product; CDC_FOLD_FINISH=0: separate kernel
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
@@ -1021,6 +1022,8 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.res = c.res; t.res_C0 = c.res_C0; t.res2 = c.res2; t.res_lo = c.res_lo; t.res2_lo = c.res2_lo;
   t.stats_in = c.stats_in; t.aff_u = c.aff_u; t.aff_c = c.aff_c; t.stats_out = c.stats_out;
   t.aff_parts = c.aff_parts;
+  t.ln_out = c.ln_out;
+  t.skip_out = c.skip_out;
   op.tc_smem = tc_smem_bytes(stage_bytes, t.stages, Nc, t.cluster_n, xsets);
   op.tc_occ = ctas_per_sm;
   op.tc_grid = std::min(tiles_total * t.n_slices * t.k_splits, e->num_sms * ctas_per_sm);
@@ -1230,6 +1233,8 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     bd.drop(c);
     x = d;
   }
+  Act xn;
+  bool have_xn = false;
   for (int l = 0; l < L - 1; ++l) {
     const Level& lv = e->ups[l];
     const int lev = L - 1 - l;
@@ -1250,7 +1255,17 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     bd.drop(bq);
     Act u = bd.new_act(lv.cout, h * 2, w * 2, true);
     std::vector<Builder::SegIn> su = {{c, 2, 2, 0, 0}};
-    bd.conv(p + "3.up", Builder::three_pass_in(su), lv.resample, EPI_BIAS, u, 1, 4);
+    Op& uop = bd.conv(p + "3.up", Builder::three_pass_in(su), lv.resample, EPI_BIAS, u, 1, 4);
+    if (l == L - 2 && lv.cout == 64 && e->mainloop == 1 && e->final_tc && e->has_f_w2 && e->final_preln) {
+      // the last Upsample feeds only the final LayerNorm + conv: its epilogue writes the normalised fp16 copy (and,
+      // outside debug mode, nothing else), so final_conv_tc_kernel has no normalisation phase
+      xn = bd.new_act(64, h * 2, w * 2);
+      have_xn = true;
+      uop.conv.ln_out = bd.ws<__half>(xn.off);
+      uop.conv.ln_g = dptr<float>(e, e->f_g);
+      uop.conv.ln_b = dptr<float>(e, e->f_b);
+      uop.conv.skip_out = e->debug_no_reuse ? 0 : 1;
+    }
     bd.drop(c);
     x = u;
   }
@@ -1266,8 +1281,10 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     // stash input pointer in conv.seg[0].src for the launcher
     op.conv.seg[0].src = bd.ws<__half>(x.off);
     op.conv.seg[1].src = bd.lo_ptr<__half>(x);
+    op.conv.seg[2].src = have_xn ? bd.ws<__half>(xn.off) : nullptr;   // pre-normalised input (tcgen05 form)
   }
   bd.drop(x);
+  if (have_xn) bd.drop(xn);
   pl->raw_off = (bd.arena_base + bd.arena.peak + 255) & ~size_t(255);
   pl->raw_bytes = 0;
   {
@@ -1277,6 +1294,18 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
       if (op.kind == OP_ATTN_CTX && op.use_tc) {
         int rc = setup_attn_tc(e, pl, op);
         if (rc) return rc;
+      }
+      if (op.kind == OP_FINAL && op.conv.seg[2].src && pl->ws) {   // halo box of the pre-normalised input
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+        cuuint32_t box[4] = {64, (cuuint32_t)kFinalPitch, (cuuint32_t)kFinalHalo, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&op.maps.a[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)op.conv.seg[2].src, gdim, gstr, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(final conv input) failed: %d", (int)r);
       }
       if (op.kind != OP_CONV) { ops2.push_back(op); continue; }
       int rc = setup_tc(e, pl, op);
@@ -1433,7 +1462,12 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         fp.clip_mode = a.clip;
         if (e->has_f_w2 && e->final_tc && e->mainloop == 1) {
           fp.Wf = dptr<__half>(e, e->f_w3);
-          launch_k(final_conv_tc_kernel, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes3, st, fp);
+          if (op.conv.seg[2].src)
+            launch_k(final_conv_tc_kernel<true>, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes3, st, fp,
+                     op.maps.a[0]);
+          else
+            launch_k(final_conv_tc_kernel<false>, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes3, st, fp,
+                     op.maps.a[0]);
         } else if (e->has_f_w2 && e->final_kx) {
           fp.Wf = dptr<__half>(e, e->f_w2);
           launch_k(final_conv_kx_kernel, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes2, st, fp);
@@ -1585,7 +1619,9 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   cudaFuncSetAttribute(gemm3xf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3xSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   cudaFuncSetAttribute(final_conv_kx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes2);
-  cudaFuncSetAttribute(final_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes3);
+  cudaFuncSetAttribute(final_conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes3);
+  cudaFuncSetAttribute(final_conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes3);
+  if (const char* v = getenv("CDC_FINAL_PRELN")) e->final_preln = atoi(v) != 0;
   if (const char* v = getenv("CDC_FINAL_TC")) e->final_tc = atoi(v) != 0;
   if (const char* v = getenv("CDC_FINAL_KX")) e->final_kx = atoi(v) != 0;
   *out = e.release();

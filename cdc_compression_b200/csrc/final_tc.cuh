@@ -16,9 +16,13 @@ namespace cdc {
 constexpr int kFinalPitch = 24;                                  // halo row pitch (pixels): 22 used
 constexpr int kFinalInBytes = kFinalHalo * kFinalPitch * 128;    // 67584
 constexpr int kFinalW3Bytes = 7 * 32 * 128;                      // [ky][32 rows n][64 c] fp16, pre-swizzled (SWIZZLE_128B)
-constexpr int kFinalSmemBytes3 = 1024 + kFinalInBytes + kFinalW3Bytes + 64;
+constexpr int kFinalSmemBytes3 = 1024 + kFinalInBytes + kFinalW3Bytes + 64;   // barriers + TMEM address word at the end
 
-__global__ void __launch_bounds__(256) final_conv_tc_kernel(const FinalParams p) {
+// PRELN: the input is already LayerNorm-ed fp16 (written by the last Upsample's epilogue, TcConvParams::ln_out): the
+// whole 22 x 24 x 64 halo tile is ONE TMA box (conv zero padding = out-of-bounds zero fill) and the kernel has no
+// normalisation phase at all.
+template <bool PRELN>
+__global__ void __launch_bounds__(256) final_conv_tc_kernel(const FinalParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -37,15 +41,25 @@ __global__ void __launch_bounds__(256) final_conv_tc_kernel(const FinalParams p)
       cp_async16(sW32 + i * 16, reinterpret_cast<const uint4*>(p.Wf) + i, 16);
     cp_async_commit();
   }
+  const uint32_t bar_in = bar + 16;             // halo tile landed (PRELN)
   if (tid == 0) {
     tc::mbar_init(bar, 1);
+    tc::mbar_init(bar_in, 1);
     tc::fence_barrier_init();
+    if (PRELN) tc::prefetch_tmap(&tmap);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  __syncthreads();   // barriers initialised before anyone polls them
   pdl_wait();
+  if (PRELN) {
+    if (tid == 0) {
+      tc::mbar_expect_tx(bar_in, (uint32_t)kFinalInBytes);
+      tc::tma_load_4d(base, &tmap, bar_in, 0, x0 - 3, y0 - 3, b);
+    }
+  } else
   // halo load + LayerNorm (as in final_conv_kernel): 8 threads per pixel, 8 channels each
   {
     const int j = tid & 7;
@@ -120,7 +134,8 @@ __global__ void __launch_bounds__(256) final_conv_tc_kernel(const FinalParams p)
     }
   }
   cp_async_wait<0>();
-  tc::fence_proxy_async();   // halo tile and weights were written through the generic proxy
+  if (PRELN) tc::mbar_wait(bar_in, 0);
+  tc::fence_proxy_async();   // weights (and, without PRELN, the halo tile) were written through the generic proxy
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();

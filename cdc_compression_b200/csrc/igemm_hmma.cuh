@@ -58,7 +58,9 @@ struct ConvParams {
   const float* aff_u;      // EPI_AFFINE: [groups][Ntot]
   const float* aff_c;
   int aff_group_stride;
-  int aff_parts;           // tcgen05 path only: aff_u / aff_c hold this many partial sums per image (else 0 / 1)
+  int aff_parts;
+  __half* ln_out;          // tcgen05 path only (see TcConvParams::ln_out)
+  int skip_out;           // tcgen05 path only: aff_u / aff_c hold this many partial sums per image (else 0 / 1)
   float2* stats_out;     // optional: LayerNorm stats of the stored output rows
 };
 

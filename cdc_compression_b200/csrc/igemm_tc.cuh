@@ -83,6 +83,11 @@ struct TcConvParams {
   // columns [s*Nc, +Nc) of every tile it visits with the fused epilogue.  For the LayerNorm epilogues the n_slices CTAs
   // of a tile form a thread-block cluster (cluster_n == n_slices) and exchange per-row partial statistics through
   // distributed shared memory (st.async + mbarrier), so no fp32 partial tile ever goes to HBM.
+  // EPI_BIAS, C_out == 64 only: additionally (or, with skip_out, instead) store fp16(LayerNorm(row) * ln_g + ln_b) to
+  // ln_out — the last Upsample feeds nothing but the final LayerNorm + 7x7 convolution, which then needs no
+  // normalisation pass of its own (final_tc.cuh).
+  __half* ln_out;
+  int skip_out;
   int cluster_n;
   int xchg_stats;            // second exchange for stats_out (row statistics of the stored LayerNorm output)
   float* raw;
@@ -752,9 +757,10 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
         const ulonglong2* vu = reinterpret_cast<const ulonglong2*>(wvec);        // affine u (per image)
         const ulonglong2* vc = reinterpret_cast<const ulonglong2*>(wvec + vs);   // affine c (per image)
         const f32x2 nmean2 = tc::pk(-st.x, -st.x), rstd2 = tc::pk(st.y, st.y);
-        for (int c0 = 0; c0 < N; c0 += 32) {
+        const bool ln_copy = EPI == EPI_BIAS && p.ln_out != nullptr;   // uniform
+        for (int c0 = 0; c0 < N && !(ln_copy && p.skip_out); c0 += 32) {
           tc::tmem_ld32(taddr + c0, v);
-          if (c0 + 32 >= N) {   // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
+          if (c0 + 32 >= N && !ln_copy) {   // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
             tc::tc_fence_before();
             tc::mbar_arrive(bar_tempty + 8 * buf);
           }
@@ -790,6 +796,62 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
           if (c0 + 32 < N) prefetch_res(c0 + 32);
           warp_store_rows64(stg, pixtab, lane, wh, out_b + c0 * 2, out_rb);
           if (has_lo) warp_store_rows64(stg, pixtab, lane, wl, out_lo_b + c0 * 2, out_rb);
+        }
+        if (ln_copy) {
+          // LayerNorm of the 64-column row (conv + bias, fp32) -> fp16 copy for the final convolution
+          const ulonglong2* vg = reinterpret_cast<const ulonglong2*>(s_vec + vs);
+          const ulonglong2* vo = reinterpret_cast<const ulonglong2*>(s_vec + 2 * vs);
+          uint32_t v1[32];
+          tc::tmem_ld32_issue(taddr, v);
+          tc::tmem_ld32_issue(taddr + 32, v1);
+          tc::tmem_wait_ld();
+          tc::tc_fence_before();
+          tc::mbar_arrive(bar_tempty + 8 * buf);
+          f32x2 x[32];
+          f32x2 s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const ulonglong2 ba = vb[i], bc = vb[8 + i];
+            x[2 * i] = tc::add2(tc::pku(v[4 * i], v[4 * i + 1]), ba.x);
+            x[2 * i + 1] = tc::add2(tc::pku(v[4 * i + 2], v[4 * i + 3]), ba.y);
+            x[16 + 2 * i] = tc::add2(tc::pku(v1[4 * i], v1[4 * i + 1]), bc.x);
+            x[16 + 2 * i + 1] = tc::add2(tc::pku(v1[4 * i + 2], v1[4 * i + 3]), bc.y);
+            s0 = tc::add2(s0, x[2 * i]);
+            s1 = tc::add2(s1, x[2 * i + 1]);
+            s2 = tc::add2(s2, x[16 + 2 * i]);
+            s3 = tc::add2(s3, x[16 + 2 * i + 1]);
+          }
+          const float2 fs = tc::upk(tc::add2(tc::add2(s0, s1), tc::add2(s2, s3)));
+          const float mean = (fs.x + fs.y) * (1.f / 64.f);
+          const f32x2 nm = tc::pk(-mean, -mean);
+          f32x2 q0 = 0ull, q1 = 0ull;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            x[2 * i] = tc::add2(x[2 * i], nm);
+            x[2 * i + 1] = tc::add2(x[2 * i + 1], nm);
+            q0 = tc::fma2(x[2 * i], x[2 * i], q0);
+            q1 = tc::fma2(x[2 * i + 1], x[2 * i + 1], q1);
+          }
+          const float2 fq = tc::upk(tc::add2(q0, q1));
+          const float rstd = 1.f / sqrtf((fq.x + fq.y) * (1.f / 64.f) + 1e-5f);
+          const f32x2 rstd2 = tc::pk(rstd, rstd);
+          uint8_t* const ln_b8 = reinterpret_cast<uint8_t*>(p.ln_out);
+#pragma unroll
+          for (int g2 = 0; g2 < 2; ++g2) {
+            uint4 wn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = g2 * 32 + j * 8;
+              const ulonglong2 g0 = vg[c >> 2], g1 = vg[(c >> 2) + 1], b0 = vo[c >> 2], b1 = vo[(c >> 2) + 1];
+              const float2 y0 = tc::upk(tc::fma2(x[g2 * 16 + j * 4], tc::mul2(rstd2, g0.x), b0.x));
+              const float2 y1 = tc::upk(tc::fma2(x[g2 * 16 + j * 4 + 1], tc::mul2(rstd2, g0.y), b0.y));
+              const float2 y2 = tc::upk(tc::fma2(x[g2 * 16 + j * 4 + 2], tc::mul2(rstd2, g1.x), b1.x));
+              const float2 y3 = tc::upk(tc::fma2(x[g2 * 16 + j * 4 + 3], tc::mul2(rstd2, g1.y), b1.y));
+              wn[j] = make_uint4(pack_half2(y0.x, y0.y), pack_half2(y1.x, y1.y), pack_half2(y2.x, y2.y),
+                                 pack_half2(y3.x, y3.y));
+            }
+            warp_store_rows64(stg, pixtab, lane, wn, ln_b8 + g2 * 64, out_rb);
+          }
         }
       } else {
         // ---- channel LayerNorm: exact two-pass statistics from the fp32 accumulator (packed fp32x2 arithmetic) ----

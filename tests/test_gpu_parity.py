@@ -336,7 +336,8 @@ KERNEL_FORMS = [("CDC_ATTN_TC", "mma.sync attention-context kernel instead of th
                 ("CDC_FINAL_KX", "49-tap final convolution instead of the horizontal-taps-in-N form"),
                 ("CDC_SLICED", "whole-row tiles at every level"),
                 ("CDC_FOLD_FINISH", "separate attn_finish_kernel instead of the fused finish epilogue"),
-                ("CDC_FINAL_TC", "mma.sync final convolution instead of the tcgen05 one")]
+                ("CDC_FINAL_TC", "mma.sync final convolution instead of the tcgen05 one"),
+                ("CDC_FINAL_PRELN", "final convolution normalises its own halo instead of reading the last Upsample's LayerNorm-ed copy")]
 
 
 @pytest.mark.parametrize("knob", [k for k, _ in KERNEL_FORMS])
