@@ -57,7 +57,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAttnTcThreads, 1)
+__global__ void __launch_bounds__(kAttnTcThreads, 2)   // <= 168 registers: two CTAs per SM at C = 64
 attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
