@@ -316,24 +316,51 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
 }
 
 // ctxn[b][d][e] = sum_c part_ctx[b][c][d][e] * exp(m_c[d]-m[d]) / sum_c part_s[b][c][d]*exp(m_c[d]-m[d])
-__global__ void attn_combine_kernel(const float* __restrict__ part_ctx, const float* __restrict__ part_m,
-                                    const float* __restrict__ part_s, int C, int nchunks,
-                                    float* __restrict__ ctxn) {
+// One CTA per (d, image).  Warp 0 turns the (<= 64) per-chunk maxima / sums of row d into normalised chunk weights
+// (lanes over chunks, shuffle reductions: fixed order, deterministic); every thread then owns columns e and adds the
+// weighted chunk partials in chunk order with four loads in flight.
+__global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_ctx,
+                                                           const float* __restrict__ part_m,
+                                                           const float* __restrict__ part_s, int C, int nchunks,
+                                                           float* __restrict__ ctxn) {
   pdl_launch_dependents();
   pdl_wait();
+  __shared__ float w_s[64];
   const int d = blockIdx.x, b = blockIdx.y;
-  const float* pm = part_m + (size_t)b * nchunks * C + d;
-  const float* ps = part_s + (size_t)b * nchunks * C + d;
-  float m = -INFINITY;
-  for (int c = 0; c < nchunks; ++c) m = fmaxf(m, pm[(size_t)c * C]);
-  float S = 0.f;
-  for (int c = 0; c < nchunks; ++c) S += ps[(size_t)c * C] * __expf(pm[(size_t)c * C] - m);
-  const float inv = 1.f / S;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const float* pm = part_m + (size_t)b * nchunks * C + d;
+    const float* ps = part_s + (size_t)b * nchunks * C + d;
+    const float m0 = lane < nchunks ? pm[(size_t)lane * C] : -INFINITY;
+    const float m1 = lane + 32 < nchunks ? pm[(size_t)(lane + 32) * C] : -INFINITY;
+    float m = fmaxf(m0, m1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float w0 = lane < nchunks ? __expf(m0 - m) : 0.f;
+    const float w1 = lane + 32 < nchunks ? __expf(m1 - m) : 0.f;
+    float S = (lane < nchunks ? ps[(size_t)lane * C] * w0 : 0.f) + (lane + 32 < nchunks ? ps[(size_t)(lane + 32) * C] * w1 : 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+    const float inv = 1.f / S;
+    w_s[lane] = w0 * inv;
+    w_s[lane + 32] = w1 * inv;
+  }
+  __syncthreads();
+  const size_t cstride = (size_t)C * C;
+  const float* src = part_ctx + (size_t)b * nchunks * cstride + (size_t)d * C;
   for (int e = threadIdx.x; e < C; e += blockDim.x) {
     float a = 0.f;
-    for (int c = 0; c < nchunks; ++c)
-      a += part_ctx[(((size_t)b * nchunks + c) * C + d) * C + e] * __expf(pm[(size_t)c * C] - m);
-    ctxn[((size_t)b * C + d) * C + e] = a * inv;
+    int c = 0;
+    for (; c + 4 <= nchunks; c += 4) {
+      const float v0 = src[(size_t)c * cstride + e], v1 = src[(size_t)(c + 1) * cstride + e];
+      const float v2 = src[(size_t)(c + 2) * cstride + e], v3 = src[(size_t)(c + 3) * cstride + e];
+      a = fmaf(v0, w_s[c], a);
+      a = fmaf(v1, w_s[c + 1], a);
+      a = fmaf(v2, w_s[c + 2], a);
+      a = fmaf(v3, w_s[c + 3], a);
+    }
+    for (; c < nchunks; ++c) a = fmaf(src[(size_t)c * cstride + e], w_s[c], a);
+    ctxn[((size_t)b * C + d) * C + e] = a;
   }
 }
 
