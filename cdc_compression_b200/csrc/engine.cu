@@ -215,6 +215,7 @@ struct cdc_engine {
   bool final_preln = true;  // last Upsample writes the LayerNorm-ed fp16 input of the final conv; CDC_FINAL_PRELN=0: final conv normalises
   bool final_tc = true; // tcgen05 form of the final conv (final_tc.cuh); CDC_FINAL_TC=0: mma.sync form
   bool fold_finish = true;   // attn_finish_kernel fused into the second C x C product; CDC_FOLD_FINISH=0: separate kernel
+  bool fuse_res = true;   // res_conv folded into block2 (second TMEM accumulator); CDC_FUSE_RES=0: separate launch
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
   bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
   int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
@@ -552,23 +553,23 @@ cudaError_t launch_igemm(const Op& op, cudaStream_t st) {
   return cudaErrorInvalidValue;
 }
 
-template <int EPI, int OCC, int N64>
+template <int EPI, int OCC, int N64, bool RT = false>
 cudaError_t launch_tc_t(const Op& op, cudaStream_t st) {
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && !attr_set[dev]) {
     // OCC only sizes the register budget; a launch may still ask for a whole SM's shared memory (one CTA per SM)
-    cudaError_t err = cudaFuncSetAttribute(igemm_tc_kernel<EPI, OCC, N64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t err = cudaFuncSetAttribute(igemm_tc_kernel<EPI, OCC, N64, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            227 * 1024);
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
   if constexpr (N64 == 2)
-    return launch_kc(igemm_tc_kernel<EPI, OCC, N64>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st,
+    return launch_kc(igemm_tc_kernel<EPI, OCC, N64, RT>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st,
                      op.tcp.cluster_n, op.maps, op.tcp, op.vecs64);
   else
-    return launch_kc(igemm_tc_kernel<EPI, OCC, N64>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st,
+    return launch_kc(igemm_tc_kernel<EPI, OCC, N64, RT>, dim3(op.tc_grid), dim3(kTcThreads), (size_t)op.tc_smem, st,
                      op.tcp.cluster_n, op.maps, op.tcp, TcNoVecs{0});
 }
 
@@ -578,9 +579,11 @@ cudaError_t launch_tc(const Op& op, cudaStream_t st) {
   if (ln && op.tcp.Nc == 64) {   // 64-column CTAs: row-in-registers LayerNorm epilogue
     if (op.tcp.Ntot == 64) {     // C_out == 64: epilogue vectors travel as kernel parameters
       if (op.tcp.epi == EPI_LN_SHIFT) return launch_tc_t<EPI_LN_SHIFT, 2, 2>(op, st);
+      if (op.tcp.res_acc) return launch_tc_t<EPI_LN_RES, 2, 2, true>(op, st);
       return launch_tc_t<EPI_LN_RES, 2, 2>(op, st);
     }
     if (op.tcp.epi == EPI_LN_SHIFT) return launch_tc_t<EPI_LN_SHIFT, 2, 1>(op, st);
+    if (op.tcp.res_acc) return launch_tc_t<EPI_LN_RES, 2, 1, true>(op, st);
     return launch_tc_t<EPI_LN_RES, 2, 1>(op, st);
   }
 #define CASE(E_)                                                \
@@ -593,6 +596,8 @@ cudaError_t launch_tc(const Op& op, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- plan builder
+constexpr int kSlicedMaxTiles = 100;  // layers with fewer 128-pixel output tiles run in sliced mode
+
 struct Builder {
   cdc_engine* e;
   Plan* pl;
@@ -697,7 +702,17 @@ struct Builder {
     // res_conv first, on the side lane: it only depends on the block input and overlaps block1
     Act r;
     bool own_r = false;
-    if (w.has_res) {
+    // tcgen05 path, 64-column CTAs (C_out == 64, or a layer that runs as fused column slices): the 1x1 res_conv is
+    // folded into block2 as extra K segments with their own TMEM accumulator (igemm_tc.cuh, res_acc) — no res_conv
+    // launch, no residual round trip through HBM.  (Wider CTAs would lose their TMEM double buffering.)
+    bool fuse_res = false;
+    if (w.has_res && e->mainloop == 1 && e->fuse_res) {
+      const int tiles_nominal = (h * wd * 8 + 127) / 128, nsl = w.cout / 64;
+      const bool fused_slices = e->sliced && e->nslice && w.cout >= 128 && nsl <= 8 && tiles_nominal < kSlicedMaxTiles &&
+                                tiles_nominal * nsl >= 64;
+      fuse_res = (w.cout == 64 || fused_slices) && 1 + three_pass_in(segs_res).size() <= (size_t)kMaxSeg;
+    }
+    if (w.has_res && !fuse_res) {
       r = new_act(w.cout, h, wd, true);
       own_r = true;
       Op& rop = conv(name + "res_conv", three_pass_in(segs_res), w.res, EPI_BIAS, r, 1, 0);
@@ -714,11 +729,26 @@ struct Builder {
     Act out = new_act(w.cout, h, wd, true);
     {
       std::vector<SegIn> s2 = {{h1, 3, 3, -1, -1}};
+      if (fuse_res)
+        for (const SegIn& t : three_pass_in(segs_res)) s2.push_back(t);
       Op& op = conv(name + "block2", s2, w.b2.conv, EPI_LN_RES, out, 1, 0);
-      op.join_before = w.has_res;
+      op.join_before = w.has_res && !fuse_res;
       op.conv.ln_g = dptr<float>(e, w.b2.g);
       op.conv.ln_b = dptr<float>(e, w.b2.b);
-      if (w.has_res) {
+      if (fuse_res) {
+        // segments 1.. are the res_conv's three passes: own weight chunks (w.res, in three_pass order), accumulator 1
+        const __half* wr = dptr<__half>(e, w.res.w);
+        size_t q = 0;
+        for (int i = 1; i < op.conv.nseg; ++i) {
+          op.conv.seg[i].acc = 1;
+          op.conv.seg[i].W = wr + q * (size_t)w.cout * 64;
+          q += (size_t)op.conv.seg[i].nchunk;
+        }
+        op.conv.res = nullptr;
+        op.conv.res_acc = 1;
+        op.conv.res_bias = w.res.bias ? dptr<float>(e, w.res.bias) : nullptr;
+        op.flops += 2.0 * w.res.macs_per_row * (double)B * h * wd;
+      } else if (w.has_res) {
         op.conv.res = ws<__half>(r.off);
         op.conv.res_lo = lo_ptr<__half>(r);
         op.conv.res_C0 = w.cout;
@@ -892,7 +922,6 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-constexpr int kSlicedMaxTiles = 100;  // layers with fewer 128-pixel output tiles run in sliced mode
 
 int pow2floor(int v) {
   int r = 1;
@@ -929,6 +958,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     t.seg[i].vr = 1;
     t.seg[i].a_bytes = 128 * a_rows;
     t.seg[i].q0 = q0;
+    t.seg[i].acc = c.seg[i].acc;
     q0 += c.seg[i].nchunk;
   }
   t.total_chunks = c.total_chunks;
@@ -972,7 +1002,11 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   const int Nc = t.Nc;
   t.n_split = Nc > 256 ? 2 : 1;
   t.n_piece = Nc / t.n_split;
-  t.nbuf = (2 * Nc <= 512) ? 2 : 1;
+  if (c.res_acc && Nc != 64)
+    return fail(e, CDC_ERR_STATE, "op %s: fused res_conv needs 64-column CTAs (builder / setup_tc slicing rules diverged)", op.name.c_str());
+  t.res_acc = c.res_acc;
+  t.res_bias = c.res_bias;
+  t.nbuf = (2 * Nc * (c.res_acc ? 2 : 1) <= 512) ? 2 : 1;
   // Nc <= 128: two CTAs per SM (2 x 256 TMEM columns, half the shared memory each) double the epilogue warps
   int ctas_per_sm = Nc <= 128 ? 2 : 1;
   // few CTAs (lowest levels): one CTA per SM with the deepest pipeline — the K loop is TMA-latency bound there
@@ -1047,6 +1081,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
       op.vecs64.bias[i] = c.bias ? host_of(c.bias)[i] : 0.f;
       op.vecs64.g[i] = c.ln_g ? host_of(c.ln_g)[i] : 1.f;
       op.vecs64.b[i] = c.ln_b ? host_of(c.ln_b)[i] : 0.f;
+      op.vecs64.rbias[i] = c.res_bias ? host_of(c.res_bias)[i] : 0.f;
     }
   }
   if (!pl->ws) return 0;  // dry run: geometry only
@@ -1076,7 +1111,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     cuuint64_t gstr[3] = {128, tap_rows * 128, (cuuint64_t)c.total_chunks * N * 128};
     cuuint32_t box[4] = {64, (cuuint32_t)t.n_piece, (cuuint32_t)t.seg[i].vr, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    void* wbase = (void*)((const __half*)c.W + (size_t)t.seg[i].q0 * N * 64);
+    void* wbase = c.seg[i].W ? (void*)c.seg[i].W : (void*)((const __half*)c.W + (size_t)t.seg[i].q0 * N * 64);
     CUresult r = enc(&op.maps.b[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, wbase, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1608,6 +1643,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
   if (const char* v = getenv("CDC_NSLICE")) e->nslice = atoi(v) != 0;
   if (const char* v = getenv("CDC_ATTN_TC")) e->attn_tc = atoi(v) != 0;
+  if (const char* v = getenv("CDC_FUSE_RES")) e->fuse_res = atoi(v) != 0;
   if (const char* v = getenv("CDC_FOLD_FINISH")) e->fold_finish = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);

@@ -16,7 +16,7 @@
 
 namespace cdc {
 
-constexpr int kMaxSeg = 6;
+constexpr int kMaxSeg = 8;
 enum EpiKind { EPI_BIAS = 0, EPI_LN_SHIFT = 1, EPI_LN_RES = 2, EPI_AFFINE = 3 };
 
 struct ConvSeg {
@@ -25,6 +25,10 @@ struct ConvSeg {
   int kh, kw;         // tap grid
   int dy0, dx0;       // input offset of tap (0,0)
   int nchunk;         // kh*kw*(C/64)
+  // tcgen05 path only: a ResnetBlock's 1x1 res_conv fused into block2 as extra K segments that accumulate into a SECOND
+  // TMEM accumulator (acc = 1); W = this segment's own weight chunks (null: the op's W + preceding chunks)
+  int acc;
+  const __half* W;
 };
 
 struct ConvParams {
@@ -59,6 +63,8 @@ struct ConvParams {
   const float* aff_c;
   int aff_group_stride;
   int aff_parts;
+  int res_acc;             // tcgen05 path only: residual = second accumulator (+ res_bias) instead of res / res2
+  const float* res_bias;
   __half* ln_out;          // tcgen05 path only (see TcConvParams::ln_out)
   int skip_out;           // tcgen05 path only: aff_u / aff_c hold this many partial sums per image (else 0 / 1)
   float2* stats_out;     // optional: LayerNorm stats of the stored output rows

@@ -33,6 +33,7 @@ struct TcSeg {
   int vr;        // vertical reuse: 1, or kh = one activation box of TH+kh-1 tile rows feeds all kh vertical taps
   int a_bytes;   // bytes of this segment's activation box
   int q0;        // first weight chunk of the segment
+  int acc;       // TMEM accumulator this segment adds to (0 = convolution, 1 = fused res_conv)
 };
 
 struct TcConvParams {
@@ -88,6 +89,11 @@ struct TcConvParams {
   // normalisation pass of its own (final_tc.cuh).
   __half* ln_out;
   int skip_out;
+  // Fused res_conv (64-column CTAs, EPI_LN_RES): segments with acc == 1 accumulate the ResnetBlock's 1x1 shortcut
+  // convolution into TMEM columns [Nc, 2Nc) of the tile's buffer; the epilogue adds them (+ res_bias) as the residual in
+  // fp32 — no separate res_conv launch, no residual round trip through HBM.
+  int res_acc;
+  const float* res_bias;
   int cluster_n;
   int xchg_stats;            // second exchange for stats_out (row statistics of the stored LayerNorm output)
   float* raw;
@@ -309,12 +315,12 @@ constexpr int kTcMaxStages = 8;
 // bytes per warp instruction) instead of one 16-byte piece per thread at a row-sized stride.
 constexpr int kEpiStageBytes = 2048;
 constexpr int kEpiPixBytes = 32 * 8;
-// bytes after the pipeline stages: epilogue vectors (bias | g | b: 3 x Nc floats), barriers, staging, pixel tables, and
+// bytes after the pipeline stages: epilogue vectors (bias | g | b | res_bias: 4 x Nc floats), barriers, staging, pixel tables, and
 // per epilogue warp 2 x Nc floats for the per-image vectors (timestep shift | attention affine u, c)
 // + cluster exchange buffers: [sets][2 (tile parity)][cluster_n][128 rows] float2
 __host__ __device__ inline int tc_xchg_bytes(int cluster_n, int sets) { return sets * 2 * cluster_n * 128 * 8; }
 __host__ __device__ inline int tc_tail_bytes(int Nc, int cluster_n = 0, int xchg_sets = 0) {
-  return 3 * Nc * 4 + 256 + 4 * (kEpiStageBytes + kEpiPixBytes) + 4 * (2 * Nc * 4) + tc_xchg_bytes(cluster_n, xchg_sets);
+  return 4 * Nc * 4 + 256 + 4 * (kEpiStageBytes + kEpiPixBytes) + 4 * (2 * Nc * 4) + tc_xchg_bytes(cluster_n, xchg_sets);
 }
 // dynamic smem: [stages][A box | B tiles] (1024-aligned) + tail
 __host__ __device__ inline int tc_stage_bytes(int b_off, int vr_max, int Nc) { return b_off + vr_max * Nc * 128; }
@@ -384,7 +390,7 @@ __device__ __forceinline__ void pack_out8(const float (&o)[8], uint4& hi, uint4&
 // Per-channel epilogue vectors of a C_out == 64 layer passed BY VALUE (kernel parameters live in the constant bank: the
 // packed arithmetic reads them through uniform registers instead of shared-memory loads on the latency-bound path).
 struct TcVecs64 {
-  float bias[64], g[64], b[64];
+  float bias[64], g[64], b[64], rbias[64];   // conv bias, LayerNorm gain / offset, bias of a fused res_conv
 };
 struct TcNoVecs {
   int unused;
@@ -392,7 +398,8 @@ struct TcNoVecs {
 
 // N64: LayerNorm epilogue specialised for 64-column CTAs (row held in registers, single TMEM pass).
 //   1 = epilogue vectors in shared memory (column slices of wider layers), 2 = vectors in the constant bank (C_out == 64).
-template <int EPI, int OCC, int N64>
+// RT: the residual is the second TMEM accumulator of a fused res_conv (TcConvParams::res_acc; 64-column CTAs only).
+template <int EPI, int OCC, int N64, bool RT = false>
 __global__ void __launch_bounds__(kTcThreads, OCC)
 igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
                 const __grid_constant__ typename std::conditional<N64 == 2, TcVecs64, TcNoVecs>::type kc) {
@@ -402,9 +409,9 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
   uint8_t* smem = smem_raw + (base - raw);
   const int stage_bytes = tc_stage_bytes(p.b_off, p.vr_max, p.Nc);
   const int vs = p.Nc;                                                     // stride of the epilogue vectors
-  float* s_vec = reinterpret_cast<float*>(smem + p.stages * stage_bytes);  // bias | g | b: 3 x Nc
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + 3 * vs * 4);
-  uint8_t* s_stage = smem + p.stages * stage_bytes + 3 * vs * 4 + 256;     // 4 x kEpiStageBytes, 4 pixel tables, 4 x 2Nc floats
+  float* s_vec = reinterpret_cast<float*>(smem + p.stages * stage_bytes);  // bias | g | b | res_bias: 4 x Nc
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + 4 * vs * 4);
+  uint8_t* s_stage = smem + p.stages * stage_bytes + 4 * vs * 4 + 256;     // 4 x kEpiStageBytes, 4 pixel tables, 4 x 2Nc floats
   // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2]; then the TMEM base address word
   const uint32_t bar_full = smem_u32(s_bar);
   const uint32_t bar_empty = bar_full + 8 * kTcMaxStages;
@@ -419,8 +426,9 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
   // fused column slice of this CTA (constant: the grid is a multiple of n_slices, units are tile-major / slice-minor)
   const bool fused_slice = EPI != EPI_RAW && p.n_slices > 1;
   const int col0 = fused_slice ? (int)(blockIdx.x % p.n_slices) * N : 0;
+  const int Nacc = p.res_acc ? 2 * N : N;   // TMEM columns of one tile buffer
   int tmem_cols = 32;
-  while (tmem_cols < p.nbuf * N) tmem_cols <<= 1;
+  while (tmem_cols < p.nbuf * Nacc) tmem_cols <<= 1;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -449,6 +457,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
     s_vec[i] = p.bias ? p.bias[col0 + i] : 0.f;
     s_vec[vs + i] = p.ln_g ? p.ln_g[col0 + i] : 1.f;
     s_vec[2 * vs + i] = p.ln_b ? p.ln_b[col0 + i] : 0.f;
+    s_vec[3 * vs + i] = p.res_bias ? p.res_bias[col0 + i] : 0.f;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -550,11 +559,13 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
       tc::mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
       c_we += CDC_CLK() - w0;
       tc::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
-      uint32_t accumulate = 0;
+      const uint32_t d_tmem0 = tmem_base + (uint32_t)(buf * Nacc);
+      uint32_t acc_started = 0;   // bit a: accumulator a already holds a partial sum of this tile
       int sc = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const int vr = p.seg[s].vr;
+        const int sacc = p.seg[s].acc;
+        const uint32_t d_tmem = d_tmem0 + (uint32_t)(sacc * N);
         const int nsc = (p.seg[s].kh / vr) * p.seg[s].kw * p.seg[s].cpt;
         for (int i = 0; i < nsc; ++i, ++sc) {
           if (sc < sc0 || sc >= sc1) continue;
@@ -562,6 +573,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
           tc::mbar_wait(bar_full + 8 * stage, phase);
           c_wf += CDC_CLK() - w1;
           tc::tc_fence_after();
+          const uint32_t accumulate = (acc_started >> sacc) & 1u;
           if (leader) {
             const uint32_t a_lo = (uint32_t)tc::make_desc_sw128(base + stage * stage_bytes);
             const uint32_t b_lo = a_lo + ((uint32_t)p.b_off >> 4);
@@ -586,7 +598,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
             tc::umma_commit(bar_empty + 8 * stage);  // frees this smem stage once the MMAs above retire
           }
           __syncwarp();
-          accumulate = 1;
+          acc_started |= 1u << sacc;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -611,7 +623,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
     uint8_t* stg = s_stage + (warp - 2) * kEpiStageBytes;
     long long* pixtab = reinterpret_cast<long long*>(s_stage + 4 * kEpiStageBytes) + (warp - 2) * 32;
     const long long out_rb = (long long)(EPI == EPI_RAW ? N : p.Ntot) * 2;   // bytes per output pixel row
-    const bool has_res = p.res != nullptr && (EPI != EPI_LN_SHIFT) && (EPI != EPI_RAW);
+    const bool has_res = !RT && p.res != nullptr && (EPI != EPI_LN_SHIFT) && (EPI != EPI_RAW);
     const bool has_lo = p.out_lo != nullptr;
     // per-image vectors (timestep shift of the tile's image | attention affine u, c): warp-private copy, fetched with
     // cp.async at the top of the tile so that its latency hides behind the accumulator wait
@@ -730,7 +742,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
         cp_async_wait<0>();
         __syncwarp();
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Nacc);
       uint32_t v[32];
       uint8_t* const out_b = reinterpret_cast<uint8_t*>(p.out + col0);
       uint8_t* const out_lo_b = reinterpret_cast<uint8_t*>(p.out_lo + col0);
@@ -870,14 +882,18 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
             return sm[q4];
           }
         };
+        const ulonglong2* vrb = reinterpret_cast<const ulonglong2*>(s_vec + 3 * vs);  // bias of a fused res_conv
         const float* c_bias = nullptr;
         const float* c_g = nullptr;
         const float* c_b = nullptr;
+        const float* c_rb = nullptr;
         if constexpr (N64 == 2) {
           c_bias = kc.bias;
           c_g = kc.g;
           c_b = kc.b;
+          c_rb = kc.rbias;
         }
+        constexpr bool res_tmem = RT && N64 != 0 && EPI == EPI_LN_RES;   // residual = second TMEM accumulator
         const ulonglong2* shift2 =
             shift_smem ? reinterpret_cast<const ulonglong2*>(wvec)
                        : (EPI == EPI_LN_SHIFT && p.shift)
@@ -910,6 +926,15 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
             f = tc::upk(tc::add2(tc::pk(o[6], o[7]), s1.y)); o[6] = f.x; o[7] = f.y;
           }
           if (has_res) add_res(j, o);
+          if (res_tmem) {   // v[] holds the 32 residual-accumulator columns of the current group
+            const ulonglong2 r0 = vec4(vrb, c_rb, c >> 2), r1 = vec4(vrb, c_rb, (c >> 2) + 1);
+            const float2 f0 = tc::upk(tc::add2(tc::pku(v[8 * j], v[8 * j + 1]), r0.x));
+            const float2 f1 = tc::upk(tc::add2(tc::pku(v[8 * j + 2], v[8 * j + 3]), r0.y));
+            const float2 f2 = tc::upk(tc::add2(tc::pku(v[8 * j + 4], v[8 * j + 5]), r1.x));
+            const float2 f3 = tc::upk(tc::add2(tc::pku(v[8 * j + 6], v[8 * j + 7]), r1.y));
+            o[0] += f0.x; o[1] += f0.y; o[2] += f1.x; o[3] += f1.y;
+            o[4] += f2.x; o[5] += f2.y; o[6] += f3.x; o[7] += f3.y;
+          }
           pack_out8(o, hi, lo, has_lo);
           if (p.stats_out) {  // statistics of the rounded values the consumer will read
             float2 f;
@@ -925,8 +950,10 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
           tc::tmem_ld32_issue(taddr, v);
           tc::tmem_ld32_issue(taddr + 32, v1);
           tc::tmem_wait_ld();
-          tc::tc_fence_before();
-          tc::mbar_arrive(bar_tempty + 8 * buf);
+          if (!res_tmem) {   // (with a fused res_conv the buffer is released after the residual columns are read)
+            tc::tc_fence_before();
+            tc::mbar_arrive(bar_tempty + 8 * buf);
+          }
           f32x2 x[32];
           f32x2 s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull;
 #pragma unroll
@@ -998,7 +1025,15 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int c0 = g * 32;
-            own_res(c0);
+            if (res_tmem) {
+              tc::tmem_ld32(taddr + 64 + c0, v);
+              if (g == 1) {
+                tc::tc_fence_before();
+                tc::mbar_arrive(bar_tempty + 8 * buf);
+              }
+            } else {
+              own_res(c0);
+            }
             uint4 wh[4], wl[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
