@@ -212,6 +212,7 @@ struct cdc_engine {
   bool final_kx = true; // final conv with the horizontal taps folded into N; CDC_FINAL_KX=0: 49-tap form
   bool has_f_w2 = false;
   size_t f_w2 = 0, f_w3 = 0;
+  size_t w_ident = 0;     // [64][64] fp16 identity "weights": identity residual of a 64-channel block through the MMA
   bool final_preln = true;  // last Upsample writes the LayerNorm-ed fp16 input of the final conv; CDC_FINAL_PRELN=0: final conv normalises
   bool final_tc = true; // tcgen05 form of the final conv (final_tc.cuh); CDC_FINAL_TC=0: mma.sync form
   bool fold_finish = true;   // attn_finish_kernel fused into the second C x C product; CDC_FOLD_FINISH=0: separate kernel
@@ -729,8 +730,20 @@ struct Builder {
     Act out = new_act(w.cout, h, wd, true);
     {
       std::vector<SegIn> s2 = {{h1, 3, 3, -1, -1}};
+      // identity residual of a 64-channel block: x_hi * I + x_lo * I into the second accumulator — the residual reaches
+      // the epilogue through TMA + two trivial MMAs, in fp32, instead of strided global loads and transpositions
+      const bool ident_res = !w.has_res && e->mainloop == 1 && e->fuse_res && w.cout == 64 && segs_res.size() == 1 &&
+                             segs_res[0].a.C == 64;
       if (fuse_res)
         for (const SegIn& t : three_pass_in(segs_res)) s2.push_back(t);
+      if (ident_res) {
+        s2.push_back(segs_res[0]);
+        if (segs_res[0].a.off_lo) {
+          SegIn t = segs_res[0];
+          t.lo = true;
+          s2.push_back(t);
+        }
+      }
       Op& op = conv(name + "block2", s2, w.b2.conv, EPI_LN_RES, out, 1, 0);
       op.join_before = w.has_res && !fuse_res;
       op.conv.ln_g = dptr<float>(e, w.b2.g);
@@ -748,6 +761,14 @@ struct Builder {
         op.conv.res_acc = 1;
         op.conv.res_bias = w.res.bias ? dptr<float>(e, w.res.bias) : nullptr;
         op.flops += 2.0 * w.res.macs_per_row * (double)B * h * wd;
+      } else if (ident_res) {
+        for (int i = 1; i < op.conv.nseg; ++i) {
+          op.conv.seg[i].acc = 1;
+          op.conv.seg[i].W = dptr<__half>(e, e->w_ident);
+        }
+        op.conv.res = nullptr;
+        op.conv.res_acc = 1;
+        op.conv.res_bias = nullptr;
       } else if (w.has_res) {
         op.conv.res = ws<__half>(r.off);
         op.conv.res_lo = lo_ptr<__half>(r);
@@ -1813,6 +1834,10 @@ int cdc_engine_finalize(cdc_engine* e) {
       memcpy(e->blob.at<__half>(e->f_w3), w3.data(), w3.size() * 2);
     }
     e->f_bias = put_f32(e, b->data.data(), cfg.channels);
+    std::vector<__half> ident((size_t)64 * 64, __float2half(0.f));
+    for (int i = 0; i < 64; ++i) ident[(size_t)i * 64 + i] = __float2half(1.f);
+    e->w_ident = e->blob.reserve(ident.size() * 2);
+    memcpy(e->blob.at<__half>(e->w_ident), ident.data(), ident.size() * 2);
   }
   e->R = (int)bcat.size();
   e->t_wcat = put_f32(e, wcat.data(), wcat.size());
