@@ -587,6 +587,7 @@ cudaError_t launch_tc(const Op& op, cudaStream_t st) {
     if (op.tcp.res_acc) return launch_tc_t<EPI_LN_RES, 2, 1, true>(op, st);
     return launch_tc_t<EPI_LN_RES, 2, 1>(op, st);
   }
+  if (op.tcp.epi == EPI_AFFINE && op.tcp.res_acc) return launch_tc_t<EPI_AFFINE, 2, 0, true>(op, st);   // C == 64
 #define CASE(E_)                                                \
   if (op.tcp.epi == E_) {                                       \
     return occ == 2 ? launch_tc_t<E_, 2, 0>(op, st) : launch_tc_t<E_, 1, 0>(op, st); \
@@ -901,6 +902,16 @@ struct Builder {
       ConvW cw;
       cw.w = 0; cw.bias = 0; cw.N = C; cw.nchunks = cb; cw.macs_per_row = 0;
       std::vector<SegIn> s = {{x, 1, 1, 0, 0}};
+      // C == 64: the residual x (hi + lo) reaches the epilogue through the MMA (identity weights, second accumulator)
+      const bool ident_res = C == 64 && e->mainloop == 1 && e->fuse_res;
+      if (ident_res) {
+        s.push_back({x, 1, 1, 0, 0});
+        if (x.off_lo) {
+          SegIn t2 = {x, 1, 1, 0, 0};
+          t2.lo = true;
+          s.push_back(t2);
+        }
+      }
       Op& op = conv(name + "out", s, cw, EPI_AFFINE, out, 1, 0);
       ConvParams& p = op.conv;
       p.W = ws<__half>(Mg);
@@ -918,6 +929,17 @@ struct Builder {
       p.res2 = nullptr;
       p.res2_lo = nullptr;
       p.bias = nullptr;
+      if (ident_res) {
+        for (int i = 1; i < p.nseg; ++i) {
+          p.seg[i].acc = 1;
+          p.seg[i].W = dptr<__half>(e, e->w_ident);
+          p.seg[i].wshared = 1;
+        }
+        p.res = nullptr;
+        p.res_lo = nullptr;
+        p.res_acc = 1;
+        p.res_bias = nullptr;
+      }
       op.grid = dim3(B * ((N + op.bm - 1) / op.bm), C / op.bn, 1);
       op.flops = 0;
     }
@@ -980,6 +1002,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     t.seg[i].a_bytes = 128 * a_rows;
     t.seg[i].q0 = q0;
     t.seg[i].acc = c.seg[i].acc;
+    t.seg[i].wshared = c.seg[i].wshared;
     q0 += c.seg[i].nchunk;
   }
   t.total_chunks = c.total_chunks;
@@ -1128,8 +1151,11 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   // one box {64, n_piece, vr, 1} brings the weight tiles of all vr vertical taps of a (kx, channel chunk).
   for (int i = 0; i < c.nseg; ++i) {
     const cuuint64_t tap_rows = (cuuint64_t)c.seg[i].kw * t.seg[i].cpt * N;
-    cuuint64_t gdim[4] = {64, tap_rows, (cuuint64_t)c.seg[i].kh, (cuuint64_t)(c.groups > 1 ? B : t.phases)};
-    cuuint64_t gstr[3] = {128, tap_rows * 128, (cuuint64_t)c.total_chunks * N * 128};
+    cuuint64_t gdim[4] = {64, tap_rows, (cuuint64_t)c.seg[i].kh,
+                          (cuuint64_t)(c.seg[i].wshared ? 1 : (c.groups > 1 ? B : t.phases))};
+    // dim 3 = output phase (transposed conv: weight sets follow each other) or image (per-image attention matrices)
+    const cuuint64_t set_stride = c.groups > 1 ? (cuuint64_t)c.w_group_stride * 2 : (cuuint64_t)c.total_chunks * N * 128;
+    cuuint64_t gstr[3] = {128, tap_rows * 128, set_stride};
     cuuint32_t box[4] = {64, (cuuint32_t)t.n_piece, (cuuint32_t)t.seg[i].vr, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     void* wbase = c.seg[i].W ? (void*)c.seg[i].W : (void*)((const __half*)c.W + (size_t)t.seg[i].q0 * N * 64);

@@ -29,6 +29,7 @@ struct ConvSeg {
   // TMEM accumulator (acc = 1); W = this segment's own weight chunks (null: the op's W + preceding chunks)
   int acc;
   const __half* W;
+  int wshared;        // with per-image weights (groups > 1): this segment's weights are shared by all images
 };
 
 struct ConvParams {

@@ -34,6 +34,7 @@ struct TcSeg {
   int a_bytes;   // bytes of this segment's activation box
   int q0;        // first weight chunk of the segment
   int acc;       // TMEM accumulator this segment adds to (0 = convolution, 1 = fused res_conv)
+  int wshared;   // per-image-weight ops only: this segment's weights are shared by all images (identity residual)
 };
 
 struct TcConvParams {
@@ -520,7 +521,8 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
                 // the weight tiles of the vr vertical taps it feeds: [piece][tap][n_piece rows]
                 for (int pc = 0; pc < p.n_split; ++pc)
                   tc::tma_load_4d(sB + pc * sg.vr * p.n_piece * 128, mB, full, 0,
-                                  (kx * sg.cpt + cc) * p.Ntot + slice * N + pc * p.n_piece, kyo, wsel);
+                                  (kx * sg.cpt + cc) * p.Ntot + slice * N + pc * p.n_piece, kyo,
+                                  sg.wshared ? 0 : wsel);
               }
               __syncwarp();
               if (++stage == p.stages) {
@@ -772,6 +774,8 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
         const bool ln_copy = EPI == EPI_BIAS && p.ln_out != nullptr;   // uniform
         for (int c0 = 0; c0 < N && !(ln_copy && p.skip_out); c0 += 32) {
           tc::tmem_ld32(taddr + c0, v);
+          uint32_t rv[RT ? 32 : 1];
+          if (RT) tc::tmem_ld32(taddr + N + c0, *reinterpret_cast<uint32_t(*)[32]>(&rv[0]));   // residual accumulator
           if (c0 + 32 >= N && !ln_copy) {   // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
             tc::tc_fence_before();
             tc::mbar_arrive(bar_tempty + 8 * buf);
@@ -803,6 +807,10 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
               o[2 * k + 1] = f.y;
             }
             if (has_res) add_res(j, o);
+            if (RT) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] += __uint_as_float(rv[RT ? j * 8 + k : 0]);
+            }
             pack_out8(o, wh[j], wl[j], has_lo);
           }
           if (c0 + 32 < N) prefetch_res(c0 + 32);
