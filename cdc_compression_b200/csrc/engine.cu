@@ -216,6 +216,7 @@ struct cdc_engine {
   bool final_preln = true;  // last Upsample writes the LayerNorm-ed fp16 input of the final conv; CDC_FINAL_PRELN=0: final conv normalises
   bool final_tc = true; // tcgen05 form of the final conv (final_tc.cuh); CDC_FINAL_TC=0: mma.sync form
   bool fold_finish = true;   // attn_finish_kernel fused into the second C x C product; CDC_FOLD_FINISH=0: separate kernel
+  int slice_max_tiles = 100;   // layers with fewer 128-pixel output tiles (at the nominal batch of 8) run in sliced mode
   bool fuse_res = true;   // res_conv folded into block2 (second TMEM accumulator); CDC_FUSE_RES=0: separate launch
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
   bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
@@ -598,7 +599,6 @@ cudaError_t launch_tc(const Op& op, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- plan builder
-constexpr int kSlicedMaxTiles = 100;  // layers with fewer 128-pixel output tiles run in sliced mode
 
 struct Builder {
   cdc_engine* e;
@@ -710,7 +710,7 @@ struct Builder {
     bool fuse_res = false;
     if (w.has_res && e->mainloop == 1 && e->fuse_res) {
       const int tiles_nominal = (h * wd * 8 + 127) / 128, nsl = w.cout / 64;
-      const bool fused_slices = e->sliced && e->nslice && w.cout >= 128 && nsl <= 8 && tiles_nominal < kSlicedMaxTiles &&
+      const bool fused_slices = e->sliced && e->nslice && w.cout >= 128 && nsl <= 8 && tiles_nominal < e->slice_max_tiles &&
                                 tiles_nominal * nsl >= 64;
       fuse_res = (w.cout == 64 || fused_slices) && 1 + three_pass_in(segs_res).size() <= (size_t)kMaxSeg;
     }
@@ -1015,9 +1015,9 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   const int tiles_nominal = ((h * w * 8 + 127) / 128) * (c.phases ? 4 : 1);
   t.Nc = N; t.n_slices = 1; t.k_splits = 1;
   // attention output GEMM (per-image weights, EPI_AFFINE): column slices only (no LayerNorm, no K split needed)
-  const bool affine_slices = e->sliced && e->nslice && op.epi == EPI_AFFINE && tiles_nominal < kSlicedMaxTiles && N >= 128;
+  const bool affine_slices = e->sliced && e->nslice && op.epi == EPI_AFFINE && tiles_nominal < e->slice_max_tiles && N >= 128;
   const bool sliceable = affine_slices ||
-                         (e->sliced && c.groups == 1 && op.epi != EPI_AFFINE && tiles_nominal < kSlicedMaxTiles && N >= 128);
+                         (e->sliced && c.groups == 1 && op.epi != EPI_AFFINE && tiles_nominal < e->slice_max_tiles && N >= 128);
   // Fused column slices (default): no K split, the fused epilogue runs in the kernel; LayerNorm epilogues exchange
   // their row statistics inside a thread-block cluster of the n_slices CTAs of a tile (<= 8: portable cluster size).
   const bool ln_epi = op.epi == EPI_LN_SHIFT || op.epi == EPI_LN_RES;
@@ -1691,6 +1691,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_NSLICE")) e->nslice = atoi(v) != 0;
   if (const char* v = getenv("CDC_ATTN_TC")) e->attn_tc = atoi(v) != 0;
   if (const char* v = getenv("CDC_FUSE_RES")) e->fuse_res = atoi(v) != 0;
+  if (const char* v = getenv("CDC_SLICE_MAXTILES")) e->slice_max_tiles = std::max(1, atoi(v));
   if (const char* v = getenv("CDC_FOLD_FINISH")) e->fold_finish = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
