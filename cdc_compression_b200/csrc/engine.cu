@@ -216,6 +216,7 @@ struct cdc_engine {
   bool final_preln = true;  // last Upsample writes the LayerNorm-ed fp16 input of the final conv; CDC_FINAL_PRELN=0: final conv normalises
   bool final_tc = true; // tcgen05 form of the final conv (final_tc.cuh); CDC_FINAL_TC=0: mma.sync form
   bool fold_finish = true;   // attn_finish_kernel fused into the second C x C product; CDC_FOLD_FINISH=0: separate kernel
+  bool dual_pass = true;   // W_hi / W_lo passes of the 3-pass convolutions share one activation load; CDC_DUAL_PASS=0: separate
   int slice_max_tiles = 100;   // layers with fewer 128-pixel output tiles (at the nominal batch of 8) run in sliced mode
   bool fuse_res = true;   // res_conv folded into block2 (second TMEM accumulator); CDC_FUSE_RES=0: separate launch
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
@@ -973,7 +974,7 @@ int pow2floor(int v) {
 }
 
 // Route a stride-1 convolution op to the tcgen05/TMA kernel: tile geometry, pipeline depth, tensor maps.
-int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
+int setup_tc(cdc_engine* e, Plan* pl, Op& op, bool allow_dual = true) {
   const ConvParams& c = op.conv;
   op.use_tc = false;
   if (e->mainloop != 1) return 0;
@@ -992,19 +993,55 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   t.tiles_b = (B + t.TB - 1) / t.TB;
   t.B = B; t.H = h; t.W = w;
   t.stride = c.stride;
-  t.nseg = c.nseg;
+  // Segments of the launch.  The (x_hi, W_hi) and (x_hi, W_lo) passes of a 3-pass trunk convolution read the same
+  // activations: outside vertical-reuse mode they are merged into one "dual" segment — one activation load per tap,
+  // two weight tiles, two MMAs (Downsample: 27 -> 18 stage loads per tile, 54 -> 36 TMA operations).
+  int khmax_all = 1;
+  for (int i = 0; i < c.nseg; ++i) khmax_all = std::max(khmax_all, c.seg[i].kh);
+  const bool dual_ok = allow_dual && e->dual_pass && c.groups == 1 && !c.phases && !(c.stride == 1 && khmax_all > 1);
+  int cq0[kMaxSeg], cidx[kMaxSeg], dual_with[kMaxSeg];
+  bool dropped[kMaxSeg];
   for (int i = 0, q0 = 0; i < c.nseg; ++i) {
-    t.seg[i].cpt = c.seg[i].C / 64;
-    t.seg[i].kh = c.seg[i].kh; t.seg[i].kw = c.seg[i].kw;
-    t.seg[i].dy0 = c.seg[i].dy0; t.seg[i].dx0 = c.seg[i].dx0;
-    t.seg[i].nchunk = c.seg[i].nchunk;
-    t.seg[i].vr = 1;
-    t.seg[i].a_bytes = 128 * a_rows;
-    t.seg[i].q0 = q0;
-    t.seg[i].acc = c.seg[i].acc;
-    t.seg[i].wshared = c.seg[i].wshared;
+    cq0[i] = q0;
     q0 += c.seg[i].nchunk;
+    dropped[i] = false;
+    dual_with[i] = -1;
   }
+  if (dual_ok)
+    for (int i = 0; i < c.nseg; ++i) {
+      if (dropped[i] || dual_with[i] >= 0 || c.seg[i].W) continue;
+      for (int j = i + 1; j < c.nseg; ++j) {
+        const ConvSeg &a = c.seg[i], &b2 = c.seg[j];
+        if (dropped[j] || b2.W || a.src != b2.src || a.C != b2.C || a.kh != b2.kh || a.kw != b2.kw || a.dy0 != b2.dy0 ||
+            a.dx0 != b2.dx0 || a.acc != b2.acc)
+          continue;
+        dual_with[i] = j;
+        dropped[j] = true;
+        break;
+      }
+    }
+  t.nseg = 0;
+  for (int i = 0; i < c.nseg; ++i) {
+    if (dropped[i]) continue;
+    const int k = t.nseg++;
+    cidx[k] = i;
+    t.seg[k].cpt = c.seg[i].C / 64;
+    t.seg[k].kh = c.seg[i].kh; t.seg[k].kw = c.seg[i].kw;
+    t.seg[k].dy0 = c.seg[i].dy0; t.seg[k].dx0 = c.seg[i].dx0;
+    t.seg[k].nchunk = c.seg[i].nchunk;
+    t.seg[k].vr = 1;
+    t.seg[k].a_bytes = 128 * a_rows;
+    t.seg[k].q0 = cq0[i];
+    t.seg[k].acc = c.seg[i].acc;
+    t.seg[k].wshared = c.seg[i].wshared;
+    t.seg[k].dual = dual_with[i] >= 0 ? 1 : 0;
+    t.seg[k].nw = t.seg[k].dual ? 2 : 1;
+    t.seg[k].avstep = 0;
+  }
+  int dual_set_chunks[kMaxSeg];   // chunks between the W_hi and W_lo tiles of a dual segment
+  for (int k = 0; k < t.nseg; ++k) dual_set_chunks[k] = t.seg[k].dual ? cq0[dual_with[cidx[k]]] - cq0[cidx[k]] : 0;
+  bool any_dual = false;
+  for (int k = 0; k < t.nseg; ++k) any_dual |= t.seg[k].dual != 0;
   t.total_chunks = c.total_chunks;
   t.Ntot = N;
   // Sliced mode for layers that cannot fill the GPU with 128-pixel tiles: 64-column slices x K splits, fp32
@@ -1060,17 +1097,20 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     return (227 * 1024) / ctas - 1024 - tc_tail_bytes(Nc, t.cluster_n, xsets) - (ctas > 1 ? 1024 : 0);
   };
   int budget = smem_budget(ctas_per_sm);
+  // two weight tiles per stage must still leave a two-stage pipeline (wide un-sliced layers): else plain 3-pass form
+  if (any_dual && budget / tc_stage_bytes(16384, 2, Nc) < 2) return setup_tc(e, pl, op, false);
   // Vertical reuse: one activation box of TH+kh-1 tile rows serves all kh vertical taps of a (kx, channel chunk) —
   // tap ky reads it TW pixel rows further down, which is a whole number of 1024-byte swizzle atoms when TW is
   // 8 or 16.  Cuts the L2->SM activation traffic of a 3x3 conv from 9 to 3.75 tile loads (the top levels are
   // L2-bandwidth bound).  Needs one image per tile and >= 2 pipeline stages of (box + kh weight tiles).
   t.b_off = 16384;
-  t.vr_max = 1;
-  t.total_sc = c.total_chunks;
+  t.vr_max = any_dual ? 2 : 1;
+  t.total_sc = 0;
+  for (int k = 0; k < t.nseg; ++k) t.total_sc += t.seg[k].nchunk;
   const bool vr_ok = e->vreuse && c.stride == 1 && t.TB == 1 && (t.TW == 8 || t.TW == 16) && a_rows == 128;
   if (vr_ok) {
     int khmax = 1;
-    for (int i = 0; i < c.nseg; ++i) khmax = std::max(khmax, c.seg[i].kh);
+    for (int i = 0; i < t.nseg; ++i) khmax = std::max(khmax, t.seg[i].kh);
     const int b_off = ((128 * t.TW * (t.TH + khmax - 1)) + 1023) & ~1023;
     if (khmax > 1 && budget / tc_stage_bytes(b_off, khmax, Nc) < 2 && e->vreuse >= 2 && ctas_per_sm == 2 &&
         smem_budget(1) / tc_stage_bytes(b_off, khmax, Nc) >= 2) {
@@ -1081,10 +1121,12 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
       t.b_off = b_off;
       t.vr_max = khmax;
       t.total_sc = 0;
-      for (int i = 0; i < c.nseg; ++i) {
-        t.seg[i].vr = c.seg[i].kh;
-        t.seg[i].a_bytes = 128 * t.TW * (t.TH + c.seg[i].kh - 1);
-        t.total_sc += c.seg[i].kw * t.seg[i].cpt;
+      for (int i = 0; i < t.nseg; ++i) {   // (no dual segments in this mode: dual_ok excludes it)
+        t.seg[i].vr = t.seg[i].kh;
+        t.seg[i].nw = t.seg[i].kh;
+        t.seg[i].avstep = (t.TW * 128) >> 4;
+        t.seg[i].a_bytes = 128 * t.TW * (t.TH + t.seg[i].kh - 1);
+        t.total_sc += t.seg[i].kw * t.seg[i].cpt;
       }
     }
   }
@@ -1131,8 +1173,9 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
   if (!pl->ws) return 0;  // dry run: geometry only
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  for (int i = 0; i < c.nseg; ++i) {
-    const cuuint64_t Cs = (cuuint64_t)c.seg[i].C;
+  for (int i = 0; i < t.nseg; ++i) {
+    const ConvSeg& cs = c.seg[cidx[i]];
+    const cuuint64_t Cs = (cuuint64_t)cs.C;
     const cuuint64_t ws_ = (cuuint64_t)c.Ws, hs_ = (cuuint64_t)c.Hs;
     cuuint64_t gdim[4] = {Cs, ws_, hs_, (cuuint64_t)B};
     cuuint64_t gstr[3] = {Cs * 2, ws_ * Cs * 2, hs_ * ws_ * Cs * 2};
@@ -1141,30 +1184,34 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op) {
     const cuuint32_t sx = (cuuint32_t)c.stride;
     cuuint32_t box[4] = {64, (cuuint32_t)t.TW * sx, (cuuint32_t)(t.TH + t.seg[i].vr - 1) * sx, (cuuint32_t)t.TB};
     cuuint32_t estr[4] = {1, sx, sx, 1};
-    CUresult r = enc(&op.maps.a[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)c.seg[i].src, gdim, gstr, box, estr,
+    CUresult r = enc(&op.maps.a[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)cs.src, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(A, op %s, seg %d) failed: %d", op.name.c_str(), i, (int)r);
   }
-  for (int i = c.nseg; i < kMaxSeg; ++i) op.maps.a[i] = op.maps.a[0];
+  for (int i = t.nseg; i < kMaxSeg; ++i) op.maps.a[i] = op.maps.a[0];
   // Weights [phase | image][chunk q][C_out][64]: per segment a 4-D view {64, kw*cpt*C_out, kh, phase | image} so that
   // one box {64, n_piece, vr, 1} brings the weight tiles of all vr vertical taps of a (kx, channel chunk).
-  for (int i = 0; i < c.nseg; ++i) {
-    const cuuint64_t tap_rows = (cuuint64_t)c.seg[i].kw * t.seg[i].cpt * N;
-    cuuint64_t gdim[4] = {64, tap_rows, (cuuint64_t)c.seg[i].kh,
-                          (cuuint64_t)(c.seg[i].wshared ? 1 : (c.groups > 1 ? B : t.phases))};
-    // dim 3 = output phase (transposed conv: weight sets follow each other) or image (per-image attention matrices)
-    const cuuint64_t set_stride = c.groups > 1 ? (cuuint64_t)c.w_group_stride * 2 : (cuuint64_t)c.total_chunks * N * 128;
+  for (int i = 0; i < t.nseg; ++i) {
+    const ConvSeg& cs = c.seg[cidx[i]];
+    const cuuint64_t tap_rows = (cuuint64_t)cs.kw * t.seg[i].cpt * N;
+    const bool dual = t.seg[i].dual != 0;
+    cuuint64_t gdim[4] = {64, tap_rows, (cuuint64_t)cs.kh,
+                          (cuuint64_t)(dual ? 2 : (cs.wshared ? 1 : (c.groups > 1 ? B : t.phases)))};
+    // dim 3 = output phase (transposed conv: weight sets follow each other), image (per-image attention matrices), or
+    // the (W_hi, W_lo) pair of a dual segment
+    const cuuint64_t set_stride = dual ? (cuuint64_t)dual_set_chunks[i] * N * 128
+                                       : (c.groups > 1 ? (cuuint64_t)c.w_group_stride * 2 : (cuuint64_t)c.total_chunks * N * 128);
     cuuint64_t gstr[3] = {128, tap_rows * 128, set_stride};
-    cuuint32_t box[4] = {64, (cuuint32_t)t.n_piece, (cuuint32_t)t.seg[i].vr, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)t.n_piece, (cuuint32_t)t.seg[i].vr, (cuuint32_t)(dual ? 2 : 1)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    void* wbase = c.seg[i].W ? (void*)c.seg[i].W : (void*)((const __half*)c.W + (size_t)t.seg[i].q0 * N * 64);
+    void* wbase = cs.W ? (void*)cs.W : (void*)((const __half*)c.W + (size_t)t.seg[i].q0 * N * 64);
     CUresult r = enc(&op.maps.b[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, wbase, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(B, op %s, seg %d) failed: %d", op.name.c_str(), i, (int)r);
   }
-  for (int i = c.nseg; i < kMaxSeg; ++i) op.maps.b[i] = op.maps.b[0];
+  for (int i = t.nseg; i < kMaxSeg; ++i) op.maps.b[i] = op.maps.b[0];
   return 0;
 }
 
@@ -1691,6 +1738,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_NSLICE")) e->nslice = atoi(v) != 0;
   if (const char* v = getenv("CDC_ATTN_TC")) e->attn_tc = atoi(v) != 0;
   if (const char* v = getenv("CDC_FUSE_RES")) e->fuse_res = atoi(v) != 0;
+  if (const char* v = getenv("CDC_DUAL_PASS")) e->dual_pass = atoi(v) != 0;
   if (const char* v = getenv("CDC_SLICE_MAXTILES")) e->slice_max_tiles = std::max(1, atoi(v));
   if (const char* v = getenv("CDC_FOLD_FINISH")) e->fold_finish = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;

@@ -35,6 +35,10 @@ struct TcSeg {
   int q0;        // first weight chunk of the segment
   int acc;       // TMEM accumulator this segment adds to (0 = convolution, 1 = fused res_conv)
   int wshared;   // per-image-weight ops only: this segment's weights are shared by all images (identity residual)
+  // weight tiles per pipeline stage and the distance (descriptor units) between the activation views they multiply:
+  //   vertical reuse: nw = vr, avstep = one tile row of pixels;   dual: nw = 2, avstep = 0 — the W_hi and W_lo passes of
+  //   a 3-pass ("trunk") convolution share one activation load (x_hi) and issue two MMAs from it
+  int nw, avstep, dual;
 };
 
 struct TcConvParams {
@@ -501,7 +505,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
         const TcSeg sg = p.seg[s];
         const CUtensorMap* mA = &maps.a[s];
         const CUtensorMap* mB = &maps.b[s];
-        const uint32_t tx_bytes = (uint32_t)(sg.a_bytes + sg.vr * N * 128);
+        const uint32_t tx_bytes = (uint32_t)(sg.a_bytes + sg.nw * N * 128);
         for (int kyo = 0; kyo < sg.kh; kyo += sg.vr)
           for (int kx = 0; kx < sg.kw; ++kx)
             for (int cc = 0; cc < sg.cpt; ++cc, ++sc) {
@@ -520,9 +524,9 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
                                 y0 * p.stride + kyo + sg.dy0 + dyp, b0);
                 // the weight tiles of the vr vertical taps it feeds: [piece][tap][n_piece rows]
                 for (int pc = 0; pc < p.n_split; ++pc)
-                  tc::tma_load_4d(sB + pc * sg.vr * p.n_piece * 128, mB, full, 0,
+                  tc::tma_load_4d(sB + pc * sg.nw * p.n_piece * 128, mB, full, 0,
                                   (kx * sg.cpt + cc) * p.Ntot + slice * N + pc * p.n_piece, kyo,
-                                  sg.wshared ? 0 : wsel);
+                                  (sg.wshared || sg.dual) ? 0 : wsel);
               }
               __syncwarp();
               if (++stage == p.stages) {
@@ -566,6 +570,8 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
       int sc = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const int vr = p.seg[s].vr;
+        const int nw = p.seg[s].nw;
+        const uint32_t avs = (uint32_t)p.seg[s].avstep;
         const int sacc = p.seg[s].acc;
         const uint32_t d_tmem = d_tmem0 + (uint32_t)(sacc * N);
         const int nsc = (p.seg[s].kh / vr) * p.seg[s].kw * p.seg[s].cpt;
@@ -580,21 +586,22 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
             const uint32_t a_lo = (uint32_t)tc::make_desc_sw128(base + stage * stage_bytes);
             const uint32_t b_lo = a_lo + ((uint32_t)p.b_off >> 4);
             if (p.n_split == 1) {
-              for (int v = 0; v < vr; ++v) {
-                // vertical tap v reads the same box TW pixel rows (a multiple of the swizzle atom) further down
-                const uint32_t av = a_lo + v * a_vstep, bv = b_lo + v * b_step;
+              for (int v = 0; v < nw; ++v) {
+                // vertical tap v reads the same box TW pixel rows (a multiple of the swizzle atom) further down;
+                // the two weight sets of a dual segment read the same view
+                const uint32_t av = a_lo + v * avs, bv = b_lo + v * b_step;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   tc::umma_f16_lo(d_tmem, av + ks * 2, bv + ks * 2, desc_hi, idesc,
                                   (ks == 0 && v == 0) ? accumulate : 1u);
               }
             } else {
-              for (int v = 0; v < vr; ++v)
+              for (int v = 0; v < nw; ++v)
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   for (int pc = 0; pc < p.n_split; ++pc)
-                    tc::umma_f16_lo(d_tmem + pc * p.n_piece, a_lo + v * a_vstep + ks * 2,
-                                    b_lo + (pc * vr + v) * b_step + ks * 2, desc_hi, idesc,
+                    tc::umma_f16_lo(d_tmem + pc * p.n_piece, a_lo + v * avs + ks * 2,
+                                    b_lo + (pc * nw + v) * b_step + ks * 2, desc_hi, idesc,
                                     (ks == 0 && v == 0) ? accumulate : 1u);
             }
             tc::umma_commit(bar_empty + 8 * stage);  // frees this smem stage once the MMAs above retire

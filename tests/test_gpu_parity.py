@@ -337,6 +337,7 @@ KERNEL_FORMS = [("CDC_ATTN_TC", "mma.sync attention-context kernel instead of th
                 ("CDC_SLICED", "whole-row tiles at every level"),
                 ("CDC_FOLD_FINISH", "separate attn_finish_kernel instead of the fused finish epilogue"),
                 ("CDC_FINAL_TC", "mma.sync final convolution instead of the tcgen05 one"),
+                ("CDC_DUAL_PASS", "separate W_hi / W_lo passes instead of one activation load feeding two weight tiles"),
                 ("CDC_FUSE_RES", "separate res_conv launches instead of the second TMEM accumulator in block2"),
                 ("CDC_FINAL_PRELN", "final convolution normalises its own halo instead of reading the last Upsample's LayerNorm-ed copy")]
 
