@@ -1313,10 +1313,16 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     std::vector<Builder::SegIn> s1, sr;
     const bool has_ctx = (l < L - 1) && (l < cfg.n_context);
     if (l == 0) {
-      s1.push_back({x, 7, 1, -3, 0});
+      // the 7 vertical taps as three K segments of 3 + 2 + 2 rows (same weight chunk order): each fits the vertical-
+      // reuse pipeline of the 3x3 convolutions (one activation box per segment and kx instead of one per tap)
+      s1.push_back({x, 3, 1, -3, 0});
+      s1.push_back({x, 2, 1, 0, 0});
+      s1.push_back({x, 2, 1, 2, 0});
       sr.push_back({x, 1, 1, 0, 0, false, true});
       if (has_ctx && !e->fold_ctx0) {
-        s1.push_back({ctx_act(0), 7, 7, -3, -3});
+        s1.push_back({ctx_act(0), 3, 7, -3, -3});
+        s1.push_back({ctx_act(0), 2, 7, 0, -3});
+        s1.push_back({ctx_act(0), 2, 7, 2, -3});
         sr.push_back({ctx_act(0), 1, 1, 0, 0});
       }
     } else {
