@@ -14,6 +14,13 @@
 //     two-pass variance from the fp32 accumulator), ReLU, timestep shift or residual, fp16 NHWC store.
 //   * persistent CTAs walk tiles with a static stride; the accumulator is double-buffered in TMEM when
 //     2*C_out <= 512 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * pipeline stages carry one activation box and 1..3 weight tiles: vertical reuse (one box of TH+kh-1 tile rows
+//     feeds all kh vertical taps) or a "dual" stage (x_hi feeds the W_hi and W_lo tiles of a 3-pass convolution).
+//   * K segments may accumulate into a SECOND TMEM accumulator: a ResnetBlock's res_conv, or the identity residual
+//     as x_hi*I + x_lo*I — the epilogue then takes the residual from TMEM in fp32 (RT) instead of global memory.
+//   * epilogue global I/O is row-contiguous through per-warp staging buffers; arithmetic in packed fp32 pairs; 64-
+//     column CTAs keep the whole row in registers (N64); low-resolution layers run as 64-column slices whose CTAs form a
+//     thread-block cluster and exchange LayerNorm statistics over distributed shared memory.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue (TMEM lane quadrant = warp%4).
 #pragma once
 #include <cuda.h>
@@ -549,7 +556,6 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
     const bool leader = tc::elect_one();
     const uint32_t idesc = tc::make_idesc_f16(p.n_piece);
     const uint32_t desc_hi = (uint32_t)(tc::make_desc_sw128(0) >> 32);
-    const uint32_t a_vstep = (uint32_t)(p.TW * 128) >> 4;        // one tile row of pixels, in descriptor units
     const uint32_t b_step = (uint32_t)(p.n_piece * 128) >> 4;    // one weight tile
     int stage = 0;
     uint32_t phase = 0;
