@@ -921,6 +921,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
                              ? reinterpret_cast<const ulonglong2*>(p.shift + (size_t)(valid ? bb : 0) * p.shift_stride + col0)
                              : nullptr;
         float osum = 0.f, osq = 0.f;
+        f32x2 os2 = 0ull, oq2 = 0ull;
         float mean, rstd;
         // finish 8 columns [c, c+8) of the row from their centred values d[0..3] (pairs) -> fp16 hi / lo pieces
         auto finish8 = [&](const f32x2 (&d)[4], int c, int j, uint4& hi, uint4& lo, f32x2 rstd2) {
@@ -957,12 +958,13 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
             o[4] += f2.x; o[5] += f2.y; o[6] += f3.x; o[7] += f3.y;
           }
           pack_out8(o, hi, lo, has_lo);
-          if (p.stats_out) {  // statistics of the rounded values the consumer will read
+          if (p.stats_out) {  // statistics of the rounded values the consumer will read (packed accumulators)
             float2 f;
-            f = unpack_half2(hi.x); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
-            f = unpack_half2(hi.y); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
-            f = unpack_half2(hi.z); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
-            f = unpack_half2(hi.w); osum += f.x + f.y; osq += f.x * f.x + f.y * f.y;
+            f32x2 h2;
+            f = unpack_half2(hi.x); h2 = tc::pk(f.x, f.y); os2 = tc::add2(os2, h2); oq2 = tc::fma2(h2, h2, oq2);
+            f = unpack_half2(hi.y); h2 = tc::pk(f.x, f.y); os2 = tc::add2(os2, h2); oq2 = tc::fma2(h2, h2, oq2);
+            f = unpack_half2(hi.z); h2 = tc::pk(f.x, f.y); os2 = tc::add2(os2, h2); oq2 = tc::fma2(h2, h2, oq2);
+            f = unpack_half2(hi.w); h2 = tc::pk(f.x, f.y); os2 = tc::add2(os2, h2); oq2 = tc::fma2(h2, h2, oq2);
           }
         };
         if (N64) {
@@ -1121,6 +1123,11 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
             warp_store_rows64(stg, pixtab, lane, wh, out_b + c0 * 2, out_rb);
             if (has_lo) warp_store_rows64(stg, pixtab, lane, wl, out_lo_b + c0 * 2, out_rb);
           }
+        }
+        if (p.stats_out) {
+          const float2 fs = tc::upk(os2), fq = tc::upk(oq2);
+          osum = fs.x + fs.y;
+          osq = fq.x + fq.y;
         }
         if (N64 && p.cluster_n > 1 && p.xchg_stats) {   // row statistics of the stored output over all column slices
           const int par = it & 1;
