@@ -1157,6 +1157,11 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op, bool allow_dual = true) {
     else pl->raw_bytes = std::max(pl->raw_bytes, need);
     t.raw = nullptr;
   }
+  t.fd_upt = make_fastdiv((uint32_t)(t.n_slices * t.k_splits));
+  t.fd_ks = make_fastdiv((uint32_t)t.k_splits);
+  t.fd_tpp = make_fastdiv((uint32_t)(t.tiles_x * t.tiles_y * t.tiles_b));
+  t.fd_txy = make_fastdiv((uint32_t)(t.tiles_x * t.tiles_y));
+  t.fd_tx = make_fastdiv((uint32_t)t.tiles_x);
   op.tcp = t;
   op.use_tc = true;
   if (ln_epi && N == 64) {   // host copies of the epilogue vectors (the blob's host image mirrors the device blob)

@@ -48,12 +48,31 @@ struct TcSeg {
   int nw, avstep, dual;
 };
 
+// Division by a launch-constant divisor without the ~35-instruction integer-division sequence (the tile loops of all
+// three warp roles decode a tile index with five of them):  q = (umulhi(n, mul) + n) >> shr,  n < 2^31.
+struct FastDiv {
+  uint32_t mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{1u, 0u};
+  if (d <= 1) return f;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.shr = s;
+  f.mul = (uint32_t)((((1ull << s) - d) << 32) / d + 1ull);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, FastDiv d) {
+  return (int)((__umulhi((uint32_t)n, d.mul) + (uint32_t)n) >> d.shr);
+}
+
 struct TcConvParams {
   int TW, TH, TB;            // tile = TB x TH x TW <= 128 pixels (rows beyond it are masked)
   int b_off;                 // byte offset of the weight tiles inside a pipeline stage (>= largest activation box)
   int vr_max;                // weight tiles per stage
   int total_sc;              // pipeline stages' worth of work per tile ("super-chunks"), split by k_splits
   int tiles_x, tiles_y, tiles_b;
+  FastDiv fd_upt, fd_ks, fd_tpp, fd_txy, fd_tx;   // units per tile, K splits, tiles per phase, tiles_x*tiles_y, tiles_x
   int B, H, W;               // tile-space (output) extents; source pixel = stride * tile pixel + tap offset
   int stride;
   int nseg;
@@ -495,15 +514,15 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
     long long c_wait = 0, c_n = 0;
     const long long c_t0 = CDC_CLK();
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const int t = u / units_per_tile;
+      const int t = fdiv(u, p.fd_upt);
       const int su = u - t * units_per_tile;
-      const int slice = su / p.k_splits, ksp = su - slice * p.k_splits;
-      const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
-      const int ph = t / tiles_per_phase;
+      const int slice = fdiv(su, p.fd_ks), ksp = su - slice * p.k_splits;
+      const int sc0 = fdiv(ksp * p.total_sc, p.fd_ks), sc1 = fdiv((ksp + 1) * p.total_sc, p.fd_ks);
+      const int ph = fdiv(t, p.fd_tpp);
       int r = t - ph * tiles_per_phase;
-      const int tb = r / (p.tiles_x * p.tiles_y);
+      const int tb = fdiv(r, p.fd_txy);
       r -= tb * p.tiles_x * p.tiles_y;
-      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int ty = fdiv(r, p.fd_tx), tx = r - ty * p.tiles_x;
       const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB;
       const int dyp = p.phases > 1 ? (ph >> 1) - 1 : 0, dxp = p.phases > 1 ? (ph & 1) - 1 : 0;
       const int wsel = p.phases > 1 ? ph : (p.w_rows_per_image ? b0 : 0);   // weight set: phase | image
@@ -563,10 +582,10 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
     long long c_wf = 0, c_we = 0;
     const long long c_t0 = CDC_CLK();
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
-      const int ksp = u % p.k_splits;
-      const int sc0 = (ksp * p.total_sc) / p.k_splits, sc1 = ((ksp + 1) * p.total_sc) / p.k_splits;
-      const int buf = it % p.nbuf;
-      const uint32_t use = (uint32_t)(it / p.nbuf);  // how many times this buffer was used before
+      const int ksp = u - fdiv(u, p.fd_ks) * p.k_splits;
+      const int sc0 = fdiv(ksp * p.total_sc, p.fd_ks), sc1 = fdiv((ksp + 1) * p.total_sc, p.fd_ks);
+      const int buf = p.nbuf == 2 ? (it & 1) : 0;
+      const uint32_t use = (uint32_t)(p.nbuf == 2 ? (it >> 1) : it);  // how many times this buffer was used before
       const long long w0 = CDC_CLK();
       tc::mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
       c_we += CDC_CLK() - w0;
@@ -650,14 +669,14 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
     const long long c_t0 = CDC_CLK();
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
       const long long i0 = CDC_CLK();
-      const int t = u / units_per_tile;
-      const int buf = it % p.nbuf;
-      const uint32_t use = (uint32_t)(it / p.nbuf);
-      const int ph = t / tiles_per_phase;
+      const int t = fdiv(u, p.fd_upt);
+      const int buf = p.nbuf == 2 ? (it & 1) : 0;
+      const uint32_t use = (uint32_t)(p.nbuf == 2 ? (it >> 1) : it);
+      const int ph = fdiv(t, p.fd_tpp);
       int r = t - ph * tiles_per_phase;
-      const int tb = r / (p.tiles_x * p.tiles_y);
+      const int tb = fdiv(r, p.fd_txy);
       r -= tb * p.tiles_x * p.tiles_y;
-      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int ty = fdiv(r, p.fd_tx), tx = r - ty * p.tiles_x;
       const int xx = tx * p.TW + lx, yy = ty * p.TH + ly, bb = tb * p.TB + lb;
       const bool valid = xx < p.W && yy < p.H && lb < p.TB && bb < p.B;
       const int py = p.phases > 1 ? (ph >> 1) : 0, px = p.phases > 1 ? (ph & 1) : 0;
@@ -764,7 +783,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
 
       if (EPI == EPI_RAW) {
         const int su = u - t * units_per_tile;
-        const int slice = su / p.k_splits, ksp = su - slice * p.k_splits;
+        const int slice = fdiv(su, p.fd_ks), ksp = su - slice * p.k_splits;
         uint8_t* dst = reinterpret_cast<uint8_t*>(p.raw + (size_t)ksp * p.raw_split_stride + slice * N);
         const long long raw_rb = (long long)p.Ntot * 4;
         for (int c0 = 0; c0 < N; c0 += 32) {
