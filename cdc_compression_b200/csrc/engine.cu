@@ -1545,7 +1545,8 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 64);
         const float* c0 = e->fold_ctx0 ? reinterpret_cast<const float*>(pl->ws + pl->ctx_off[0]) : nullptr;
         launch_k(pack_input_kernel, dim3(blocks), dim3(256), 0, st, a.x, (int)cfg.channels, c0,
-                 (int)(e->fold_ctx0 ? cfg.context_channels : 0), B, H, W, const_cast<__half*>(op.dbg));
+                 (int)(e->fold_ctx0 ? cfg.context_channels : 0), B, H, W, make_fastdiv((uint32_t)W),
+                 make_fastdiv((uint32_t)H), const_cast<__half*>(op.dbg));
         break;
       }
       case OP_CONV: {

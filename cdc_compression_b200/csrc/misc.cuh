@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/cdc_b200.h"
 #include "common.cuh"
+#include "igemm_tc.cuh"   // FastDiv
 
 namespace cdc {
 
@@ -13,17 +14,17 @@ namespace cdc {
 //   remainders there, the 7x7 conv has zero weights for it.  Channels >= cx+cc of every slot are zero.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_input_kernel(const float* __restrict__ x, int cx, const float* __restrict__ ctx, int cc,
-                                  int B, int H, int W, __half* __restrict__ out) {
+                                  int B, int H, int W, FastDiv fdW, FastDiv fdH, __half* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   const int total = B * H * W * 8;   // < 2^31 for every supported shape (checked by the engine)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int kx = i & 7;
     const int pix = i >> 3;
-    const int xx = pix % W;
-    const int t = pix / W;
-    const int yy = t % H;
-    const int b = t / H;
+    const int t = fdiv(pix, fdW);
+    const int xx = pix - t * W;
+    const int b = fdiv(t, fdH);
+    const int yy = t - b * H;
     const int sx = kx < 7 ? xx + kx - 3 : xx;   // slot 7 repeats the centre pixel (weight-remainder pass of res_conv)
     float v[8];
 #pragma unroll
