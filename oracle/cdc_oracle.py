@@ -108,6 +108,32 @@ def upsample(sd: StateDict, p: str, x: Tensor) -> Tensor:
     return F.conv_transpose2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"], stride=2, padding=1)
 
 
+def context_decode(sd: StateDict, p: str, q_latent: Tensor, cond: Optional[Tensor] = None) -> list:
+    """``context_fn.decode``: the producer of the U-Net's ``context`` list.
+
+    BigCompressor.decode (epsilonparam/modules/compress_modules.py:74-82, layers :144-156) and ResnetCompressor.decode
+    (xparam/modules/compress_modules.py:68-74, layers :142-151): per stage ResnetBlock WITHOUT time embedding ->
+    [VBRCondition: x * scale(cond) + shift(cond), 1x1 convs of the scalar cond, network_components.py:304-314, only when
+    the compressor was built with vbr=True] -> Upsample (ConvTranspose2d 4/2/1; the last stage changes the channel
+    count).  Returns the stage outputs finest first (``output[::-1]``).  ``p`` = 'context_fn.' (or '' for a bare
+    compressor state_dict)."""
+    n = _count(sd, p + "dec.")
+    x, outs = q_latent, []
+    for i in range(n):
+        x = resnet_block(sd, f"{p}dec.{i}.0.", x, None)
+        up = 1
+        if (f"{p}dec.{i}.1.scale.weight") in sd:          # vbr=True: dec.i = [ResnetBlock, VBRCondition, Upsample]
+            c = cond.reshape(-1, 1, 1, 1).to(x.dtype)
+            x = x * F.conv2d(c, sd[f"{p}dec.{i}.1.scale.weight"], sd[f"{p}dec.{i}.1.scale.bias"]) + \
+                F.conv2d(c, sd[f"{p}dec.{i}.1.shift.weight"], sd[f"{p}dec.{i}.1.shift.bias"])
+            up = 2
+        elif (f"{p}dec.{i}.2.conv.weight") in sd:         # vbr=False keeps an nn.Identity at index 1 (no parameters)
+            up = 2
+        x = upsample(sd, f"{p}dec.{i}.{up}.", x)
+        outs.append(x)
+    return outs[::-1]
+
+
 def time_embedding(sd: StateDict, time: Tensor) -> Tensor:
     """Linear(1,4*dim) -> GELU(erf) -> Linear(4*dim, dim) on a [B,1] float time."""
     t = F.linear(time, sd["time_mlp.0.weight"], sd["time_mlp.0.bias"])

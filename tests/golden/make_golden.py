@@ -28,6 +28,10 @@ CASES = [  # name, variant, B, H, W, seed, gain
     ("eps_b1_32x32_smallgain", "eps", 1, 32, 32, 1, 0.5),
     ("x_b1_96x64", "x", 1, 96, 64, 1, 1.0),
 ]
+CTXDEC = [  # name, variant, B, H, W, seed   (context_fn.decode: SURVEY.md section 8 (f), row 1)
+    ("eps_b1_32x64", "eps", 1, 32, 64, 0),
+    ("x_b1_32x64", "x", 1, 32, 64, 1),
+]
 LOOPS = [  # name, variant, B, H, W, S, seed
     ("eps_loop_s6", "eps", 2, 64, 64, 6, 0),
     ("x_loop_s5", "x", 2, 64, 64, 5, 0),
@@ -41,6 +45,13 @@ def case_inputs(variant, B, H, W, seed):
     t = torch.linspace(0.15, 0.9, B)[:, None]
     init = torch.randn(B, 3, H, W, generator=g) * 0.8
     return x, t, ctx, init
+
+
+def ctxdec_latent(sd, B, H, W, seed):
+    """Seeded integer-valued latent with the channel count the decoder's first ResnetBlock expects (1/16 resolution)."""
+    C = sd["context_fn.dec.0.0.block1.block.0.weight"].shape[1]
+    g = torch.Generator().manual_seed(11 + seed)
+    return (torch.randn(B, C, H // 16, W // 16, generator=g) * 2).round()
 
 
 def main():
@@ -68,6 +79,15 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"loop_{name}.npz"), out=out.numpy(),
                             meta=np.array([B, H, W, S, seed], dtype=np.int64), **tables)
         print(name, tuple(out.shape), float(out.abs().max()))
+    # context_fn.decode (the producer of the U-Net's context list) on a seeded integer latent
+    for name, variant, B, H, W, seed in CTXDEC:
+        _, diff = build_reference_diffusion(variant, with_context_fn=True)
+        diff.load_state_dict(O.seeded_fill(diff.state_dict(), seed=seed, denoiser_gain=0.5))
+        q = ctxdec_latent(diff.state_dict(), B, H, W, seed)
+        outs = diff.context_fn.decode(q) if variant == "x" else diff.context_fn.decode(q, None)
+        np.savez_compressed(os.path.join(HERE, f"ctxdec_{name}.npz"), meta=np.array([B, H, W, seed], dtype=np.int64),
+                            **{f"out{i}": o.numpy() for i, o in enumerate(outs)})
+        print("ctxdec", name, [tuple(o.shape) for o in outs], float(outs[0].abs().mean()))
     # schedule-only fixtures at the demo step counts
     for variant, sched, T in (("eps", "linear", 20000), ("x", "cosine", 8193)):
         _, diff = build_reference_diffusion(variant, with_context_fn=False)

@@ -110,3 +110,40 @@ def test_oracle_equals_live_reference(variant):
     up, dn = nc.Upsample(64).double(), nc.Downsample(64).double()
     assert torch.allclose(up(xa), O.upsample({"p." + k: v for k, v in up.state_dict().items()}, "p.", xa), atol=1e-12)
     assert torch.allclose(dn(xa), O.downsample({"p." + k: v for k, v in dn.state_dict().items()}, "p.", xa), atol=1e-12)
+
+
+# ---- context_fn.decode: the producer of the U-Net's context list -------------------
+from golden.make_golden import CTXDEC, ctxdec_latent  # noqa: E402
+
+
+@pytest.mark.parametrize("case", CTXDEC, ids=[c[0] for c in CTXDEC])
+def test_context_decode_matches_reference_golden(case):
+    """oracle.context_decode (restatement of BigCompressor.decode / ResnetCompressor.decode) vs the unmodified
+    reference's outputs on a seeded integer latent; the state_dict comes from the drop-in modules, whose keys mirror the
+    reference's (so this also pins the `context_fn.dec.*` weight ABI the engine will consume for that row)."""
+    from conftest import build_dropin
+    name, variant, B, H, W, seed = case
+    gold = np.load(os.path.join(GOLD, f"ctxdec_{name}.npz"))
+    d = build_dropin(variant)
+    sd = O.seeded_fill(d.state_dict(), seed=seed, denoiser_gain=0.5)
+    outs = O.context_decode(sd, "context_fn.", ctxdec_latent(sd, B, H, W, seed))
+    assert len(outs) == 4
+    for i, o in enumerate(outs):
+        ref = torch.from_numpy(gold[f"out{i}"])
+        assert o.shape == ref.shape
+        assert (o - ref).norm() / ref.norm() < 2e-6
+    # the finest map is what the U-Net concatenates at level 0: 3 channels (eps) / 64 channels (x)
+    assert outs[0].shape[1] == (3 if variant == "eps" else 64) and outs[0].shape[-2:] == (H, W)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+@pytest.mark.parametrize("variant", ["eps", "x"])
+def test_context_decode_matches_live_reference(variant):
+    from oracle.ref_loader import build_reference_diffusion
+    _, diff = build_reference_diffusion(variant, with_context_fn=True)
+    sd = O.seeded_fill(diff.state_dict(), seed=4, denoiser_gain=0.5)
+    diff.load_state_dict(sd)
+    q = ctxdec_latent(sd, 2, 64, 32, 4)
+    ref = diff.context_fn.decode(q) if variant == "x" else diff.context_fn.decode(q, None)
+    for a, b in zip(O.context_decode(sd, "context_fn.", q), ref):
+        assert torch.equal(a, b)
