@@ -119,15 +119,17 @@ class DiffusionBase(nn.Module):
                     self.sqrt_one_minus_alphas_cumprod]
             self._coef_cpu = torch.stack([c.float() for c in cols], dim=1).cpu()
             self._coef_key = key
-            self._coef_sent = None
+            self._coef_token = object()      # identity of this table: what an engine remembers having received
         return self._coef_cpu
 
     def _bind(self, x, context, eta):
         eng = self.denoise_fn.engine_for(x.device)
         coefs = self._coef_table(eta)
-        if getattr(self, "_coef_sent", None) is not eng:
+        # the engine (not this object) remembers which table it holds: two GaussianDiffusion objects sharing one Unet
+        # can then never leave the other's schedule on the engine
+        if getattr(eng, "_sched_token", None) is not self._coef_token:
             eng.set_schedule(coefs)
-            self._coef_sent = eng
+            eng._sched_token = self._coef_token
         return eng
 
     def _advance_rng_like_reference(self, x, steps):
@@ -162,8 +164,14 @@ class DiffusionBase(nn.Module):
         return x
 
     def _single_step(self, x, t, context, eta, pred_mode, clip_mode):
-        """``ddim(x, t, ...)`` for callers that drive the loop themselves; all entries of t must be equal."""
-        i = int(t.reshape(-1)[0].item())
+        """``ddim(x, t, ...)`` for callers that drive the loop themselves.  The engine advances the whole batch at ONE
+        schedule index (the reference's own loops always do: p_sample_loop builds ``t`` with ``torch.full``), so a
+        batch with mixed timesteps raises instead of silently using t[0]."""
+        tt = t.reshape(-1)
+        if tt.numel() > 1 and not bool((tt == tt[0]).all()):
+            raise NotImplementedError("ddim() with different timesteps inside one batch is not implemented by the "
+                                      "CUDA engine: call it once per group of equal t")
+        i = int(tt[0].item())
         out = x.detach().to(torch.float32).contiguous().clone()
         eng = self._bind(out, context, eta)
         B, _, H, W = out.shape

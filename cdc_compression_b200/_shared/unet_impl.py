@@ -7,13 +7,15 @@ Same constructor arguments, module tree and ``state_dict`` keys as the reference
 """
 from __future__ import annotations
 
-import weakref
-
 import torch
 from torch import nn
 
 from ..engine import DenoiserEngine, EngineError
 from .layers import Downsample, LayerNorm, LinearAttention, PreNorm, Residual, ResnetBlock, Upsample
+
+
+def _mark_engine_dirty(module, incompatible_keys):
+    module._engine_dirty = True
 
 
 class UnetBase(nn.Module):
@@ -64,13 +66,16 @@ class UnetBase(nn.Module):
         self._with_time_emb = with_time_emb
         self._engine = None
         self._engine_dirty = True
-        ref = weakref.ref(self)
+        # the hook receives the module it fires on, so a deep copy (ema_pytorch.EMA) marks ITSELF dirty, not the original
+        self.register_load_state_dict_post_hook(_mark_engine_dirty)
 
-        def _mark(*_):
-            m = ref()
-            if m is not None:
-                m._engine_dirty = True
-        self.register_load_state_dict_post_hook(lambda module, keys: _mark())
+    def __getstate__(self):
+        """copy.deepcopy / pickle: the copy owns no engine (a ``cdc_engine`` handle must not be shared or destroyed
+        twice) and re-uploads its own weights on first use."""
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_dirty"] = True
+        return state
 
     # ---- engine lifecycle -------------------------------------------------------------------
     def _apply(self, fn, *a, **k):

@@ -108,7 +108,7 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
       tc::mbar_init(bar_pvf + 8 * i, 128);
       tc::mbar_init(bar_pve + 8 * i, 1);
     }
-    for (int i = 0; i < kAttnStatSlots; ++i) tc::mbar_init(bar_st + 8 * i, 1);
+    for (int i = 0; i < kAttnStatSlots; ++i) tc::mbar_init(bar_st + 8 * i, 32);
     tc::mbar_init(bar_fin, 1);
     tc::fence_barrier_init();
   }
@@ -159,8 +159,8 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
       float* slot = pStat + (i % kAttnStatSlots) * 128;
       *reinterpret_cast<float2*>(slot + 2 * lane) = make_float2(-st.x, -st.z);
       *reinterpret_cast<float2*>(slot + 64 + 2 * lane) = make_float2(st.y, st.w);
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_st + 8 * (i % kAttnStatSlots));
+      // every lane releases its own two stores (count 32): no reliance on __syncwarp ordering other lanes' writes
+      tc::mbar_arrive(bar_st + 8 * (i % kAttnStatSlots));
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================

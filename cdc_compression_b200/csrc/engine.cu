@@ -240,6 +240,9 @@ struct cdc_engine {
   // schedule
   cdc_step_coef* d_table = nullptr;
   int table_cap = 0, S = 0;
+  cdc_step_coef* h_table = nullptr;   // pinned staging copy of the schedule (cdc_set_schedule copies asynchronously)
+  int h_table_cap = 0;
+  cudaEvent_t ev_table = nullptr;
   int* d_step = nullptr;
   // stream the sampling loop runs on (the caller's stream may be the legacy default stream, which
   // cannot be captured); joined to the caller's stream with events on both sides
@@ -275,6 +278,22 @@ int fail(cdc_engine* e, int code, const char* fmt, ...) {
     if (_err != cudaSuccess)                                                                      \
       return fail(e, CDC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_err), __FILE__, __LINE__); \
   } while (0)
+
+// Every C-ABI entry runs on the engine's device and leaves the calling thread's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (dev < 0) return;   // planning-only engine: no device work
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 template <typename T>
 T* dptr(cdc_engine* e, size_t off) { return reinterpret_cast<T*>(e->dblob + off); }
@@ -1732,7 +1751,11 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, CDC_ERR_CUDA, "no CUDA device: the CDC engine has no CPU path");
   if (device < 0 || device >= ndev) return fail(nullptr, CDC_ERR_INVALID, "device %d out of range", device);
-  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, CDC_ERR_CUDA, "cudaSetDevice failed");
+  DeviceGuard dg(device);
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return fail(nullptr, CDC_ERR_CUDA, "cudaSetDevice failed");
+  }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) return fail(nullptr, CDC_ERR_UNSUPPORTED, "device sm_%d%d: this build targets sm_100a only", prop.major, prop.minor);
@@ -1743,7 +1766,8 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
     return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   if (cudaStreamCreateWithFlags(&e->loop_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess)
+      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_table, cudaEventDisableTiming) != cudaSuccess)
     return fail(nullptr, CDC_ERR_CUDA, "stream/event creation failed");
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
@@ -1775,7 +1799,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
 void cdc_engine_destroy(cdc_engine* e) {
   if (!e) return;
   if (e->dry) { delete e; return; }
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   for (auto& kv : e->plans) if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
   if (e->dblob) cudaFree(e->dblob);
   if (e->d_table) cudaFree(e->d_table);
@@ -1786,6 +1810,8 @@ void cdc_engine_destroy(cdc_engine* e) {
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->ev_table) { cudaEventSynchronize(e->ev_table); cudaEventDestroy(e->ev_table); }
+  if (e->h_table) cudaFreeHost(e->h_table);
   delete e;
 }
 
@@ -1802,7 +1828,7 @@ int cdc_engine_set_weight(cdc_engine* e, const char* key, const float* host_ptr,
 
 int cdc_engine_finalize(cdc_engine* e) {
   if (!e) return CDC_ERR_INVALID;
-  if (!e->dry) cudaSetDevice(e->device);
+  DeviceGuard dg(e->dry ? -1 : e->device);
   const cdc_config& cfg = e->cfg;
   const int L = cfg.n_levels, dim = cfg.dim;
   e->blob.host.clear();
@@ -1971,7 +1997,7 @@ int cdc_unet_forward(cdc_engine* e, const float* x, const float* time, const flo
                      int B, int H, int W, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!e) return CDC_ERR_INVALID;
   if (!x || !time || !out || !workspace) return fail(e, CDC_ERR_INVALID, "null pointer argument");
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   int rc;
   Plan* pl = get_plan(e, B, H, W, workspace, &rc);
   if (!pl) return rc;
@@ -1988,7 +2014,7 @@ int cdc_set_context(cdc_engine* e, const float* const* ctx, int n_ctx, int B, in
                     int64_t workspace_bytes, void* stream) {
   if (!e) return CDC_ERR_INVALID;
   if (!workspace) return fail(e, CDC_ERR_INVALID, "null workspace");
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   int rc;
   Plan* pl = get_plan(e, B, H, W, workspace, &rc);
   if (!pl) return rc;
@@ -2002,7 +2028,7 @@ int cdc_set_context(cdc_engine* e, const float* const* ctx, int n_ctx, int B, in
 int cdc_set_schedule(cdc_engine* e, const cdc_step_coef* host_coefs, int S, void* stream) {
   if (!e || !host_coefs || S < 1) return fail(e, CDC_ERR_INVALID, "bad schedule");
   if (e->dry) return fail(e, CDC_ERR_STATE, "planning-only engine (device=-1) cannot compute: there is no CPU path");
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   if (S > e->table_cap) {
     if (e->d_table) cudaFree(e->d_table);
     e->d_table = nullptr;
@@ -2011,9 +2037,20 @@ int cdc_set_schedule(cdc_engine* e, const cdc_step_coef* host_coefs, int S, void
     // graphs captured the old table pointer
     for (auto& kv : e->plans) if (kv.second->graph) { cudaGraphExecDestroy(kv.second->graph); kv.second->graph = nullptr; }
   }
-  // synchronous copy from pageable host memory: the caller's buffer may be freed right after return
-  CUDA_TRY(e, cudaStreamSynchronize((cudaStream_t)stream));
-  CUDA_TRY(e, cudaMemcpy(e->d_table, host_coefs, (size_t)S * sizeof(cdc_step_coef), cudaMemcpyHostToDevice));
+  // The caller's buffer may be freed right after return: stage it in the engine's pinned buffer and copy on the
+  // caller's stream (ordered after any decode already enqueued there).  Only a second set_schedule issued while the
+  // previous copy is still in flight waits (for that copy alone) — the stream is never synchronised.
+  if (S > e->h_table_cap) {
+    if (e->h_table) { cudaEventSynchronize(e->ev_table); cudaFreeHost(e->h_table); e->h_table = nullptr; }
+    CUDA_TRY(e, cudaHostAlloc((void**)&e->h_table, (size_t)S * sizeof(cdc_step_coef), cudaHostAllocDefault));
+    e->h_table_cap = S;
+  } else {
+    CUDA_TRY(e, cudaEventSynchronize(e->ev_table));
+  }
+  memcpy(e->h_table, host_coefs, (size_t)S * sizeof(cdc_step_coef));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_table, e->h_table, (size_t)S * sizeof(cdc_step_coef), cudaMemcpyHostToDevice,
+                              (cudaStream_t)stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev_table, (cudaStream_t)stream));
   e->S = S;
   return CDC_OK;
 }
@@ -2038,7 +2075,7 @@ int cdc_ddim_step(cdc_engine* e, float* x_inout, int i, const float* z, int pred
                   int W, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!e) return CDC_ERR_INVALID;
   if (!x_inout) return fail(e, CDC_ERR_INVALID, "null x");
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   Plan* pl;
   int rc = sampler_prologue(e, B, H, W, workspace, workspace_bytes, pred_mode, clip_mode, &pl);
   if (rc) return rc;
@@ -2054,7 +2091,7 @@ int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int 
                     int W, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!e) return CDC_ERR_INVALID;
   if (!x_inout) return fail(e, CDC_ERR_INVALID, "null x");
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   Plan* pl;
   int rc = sampler_prologue(e, B, H, W, workspace, workspace_bytes, pred_mode, clip_mode, &pl);
   if (rc) return rc;
@@ -2063,37 +2100,45 @@ int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int 
   cudaStream_t st = e->loop_stream;
   CUDA_TRY(e, cudaEventRecord(e->ev_in, caller));
   CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_in, 0));
-  int i_start = i_first;
   // the loop state lives in the workspace so the captured graph does not depend on the caller's buffer
   float* xs = reinterpret_cast<float*>(pl->ws + pl->xstate_off);
   const size_t xbytes = (size_t)B * e->cfg.channels * H * W * 4;
-  CUDA_TRY(e, cudaMemcpyAsync(xs, x_inout, xbytes, cudaMemcpyDeviceToDevice, st));
-  if (!pl->graph || pl->graph_pred != pred_mode || pl->graph_clip != clip_mode) {
-    if (pl->graph) { cudaGraphExecDestroy(pl->graph); pl->graph = nullptr; }
-    RunArgs a;
-    a.x = xs; a.x_inout = xs; a.z = nullptr; a.mode = 1; a.pred = pred_mode; a.clip = clip_mode; a.advance = true;
-    // The first step runs eagerly: it is real work AND it forces every kernel's module load /
-    // attribute setup to happen before stream capture starts.
-    set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
-    if ((rc = run_plan(e, pl, a, st))) return rc;
-    i_start = i_first - 1;
-    cudaGraph_t g = nullptr;
-    CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = run_plan(e, pl, a, st);
-    cudaError_t err = cudaStreamEndCapture(st, &g);
-    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-    if (err != cudaSuccess) return fail(e, CDC_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err));
-    err = cudaGraphInstantiate(&pl->graph, g, 0);
-    cudaGraphDestroy(g);
-    if (err != cudaSuccess) { pl->graph = nullptr; return fail(e, CDC_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(err)); }
-    pl->graph_pred = pred_mode; pl->graph_clip = clip_mode;
-  } else {
-    set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
-  }
-  for (int i = i_start; i >= i_last; --i) CUDA_TRY(e, cudaGraphLaunch(pl->graph, st));
-  CUDA_TRY(e, cudaMemcpyAsync(x_inout, xs, xbytes, cudaMemcpyDeviceToDevice, st));
-  CUDA_TRY(e, cudaEventRecord(e->ev_out, st));
-  CUDA_TRY(e, cudaStreamWaitEvent(caller, e->ev_out, 0));
+  auto body = [&]() -> int {
+    int i_start = i_first;
+    CUDA_TRY(e, cudaMemcpyAsync(xs, x_inout, xbytes, cudaMemcpyDeviceToDevice, st));
+    if (!pl->graph || pl->graph_pred != pred_mode || pl->graph_clip != clip_mode) {
+      if (pl->graph) { cudaGraphExecDestroy(pl->graph); pl->graph = nullptr; }
+      RunArgs a;
+      a.x = xs; a.x_inout = xs; a.z = nullptr; a.mode = 1; a.pred = pred_mode; a.clip = clip_mode; a.advance = true;
+      // The first step runs eagerly: it is real work AND it forces every kernel's module load /
+      // attribute setup to happen before stream capture starts.
+      set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
+      int rc2 = run_plan(e, pl, a, st);
+      if (rc2) return rc2;
+      i_start = i_first - 1;
+      cudaGraph_t g = nullptr;
+      CUDA_TRY(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc2 = run_plan(e, pl, a, st);
+      cudaError_t err = cudaStreamEndCapture(st, &g);
+      if (rc2) { if (g) cudaGraphDestroy(g); return rc2; }
+      if (err != cudaSuccess) return fail(e, CDC_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err));
+      err = cudaGraphInstantiate(&pl->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (err != cudaSuccess) { pl->graph = nullptr; return fail(e, CDC_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(err)); }
+      pl->graph_pred = pred_mode; pl->graph_clip = clip_mode;
+    } else {
+      set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
+    }
+    for (int i = i_start; i >= i_last; --i) CUDA_TRY(e, cudaGraphLaunch(pl->graph, st));
+    CUDA_TRY(e, cudaMemcpyAsync(x_inout, xs, xbytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  };
+  rc = body();
+  // success or not, the caller's stream is re-joined with everything that was enqueued on the loop stream
+  cudaError_t j1 = cudaEventRecord(e->ev_out, st);
+  cudaError_t j2 = j1 == cudaSuccess ? cudaStreamWaitEvent(caller, e->ev_out, 0) : j1;
+  if (rc) return rc;
+  if (j2 != cudaSuccess) return fail(e, CDC_ERR_CUDA, "joining the loop stream failed: %s", cudaGetErrorString(j2));
   e->last_plan = pl;
   return CDC_OK;
 }
@@ -2135,7 +2180,7 @@ int64_t cdc_engine_debug_read(cdc_engine* e, int op_index, float* host_out, int6
   if (W) *W = op.dW;
   if (!host_out) return n;
   if (capacity < n) return fail(e, CDC_ERR_INVALID, "debug buffer too small");
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   std::vector<__half> tmp((size_t)n);
   CUDA_TRY(e, cudaDeviceSynchronize());
   CUDA_TRY(e, cudaMemcpy(tmp.data(), op.dbg, (size_t)n * 2, cudaMemcpyDeviceToHost));
@@ -2149,7 +2194,7 @@ int cdc_engine_profile_ops(cdc_engine* e, int iters, float* ms_out, double* flop
   Plan* pl = e->last_plan;
   const int n = (int)pl->ops.size();
   if (capacity < n) return fail(e, CDC_ERR_INVALID, "profile buffers too small (%d ops)", n);
-  cudaSetDevice(e->device);
+  DeviceGuard dg(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t a, b;
   CUDA_TRY(e, cudaEventCreate(&a));

@@ -42,6 +42,8 @@ class DenoiserEngine:
         self.variant = variant
         self.channels = channels
         self.n_context = len(context_dim_mults)
+        # channel count of each context map: [context_channels, dim*m_0, dim*m_1, ...] (reference unet.py:28-30)
+        self.context_widths = ([int(context_channels)] + [int(dim) * int(m) for m in context_dim_mults])[:self.n_context]
         cfg = CdcConfig()
         cfg.abi_version = _native.CDC_ABI_VERSION
         cfg.variant = VARIANT[variant]
@@ -176,8 +178,11 @@ class DenoiserEngine:
         for l, c in enumerate(context):
             if c.device != self.device:
                 raise EngineError("context tensor on the wrong device")
-            if c.shape[0] != B or c.shape[2] != (H >> l) or c.shape[3] != (W >> l):
+            if c.dim() != 4 or c.shape[0] != B or c.shape[2] != (H >> l) or c.shape[3] != (W >> l):
                 raise EngineError(f"context[{l}] has shape {tuple(c.shape)}; expected spatial {(H >> l, W >> l)}")
+            if c.shape[1] != self.context_widths[l]:
+                raise EngineError(f"context[{l}] has {c.shape[1]} channels; this Unet expects "
+                                  f"{self.context_widths[l]} (context_channels / dim * context_dim_mults)")
             keep.append(c.detach().to(torch.float32).contiguous())
         arr = (C.c_void_p * len(keep))(*[c.data_ptr() for c in keep])
         return arr, keep

@@ -63,8 +63,7 @@ class GaussianDiffusion(DiffusionBase):
 
     @torch.no_grad()
     def ddim(self, x, t, context, clip_denoised, eta=0):
-        if self.pred_mode != "noise":
-            raise NotImplementedError("the eps engine implements pred_mode='noise'")
+        # like the reference (:137-152), ddim() treats the U-Net output as the noise whatever pred_mode says
         return self._single_step(x, t, context, eta, "noise", self._clip_mode(clip_denoised))
 
     @torch.no_grad()
@@ -81,8 +80,6 @@ class GaussianDiffusion(DiffusionBase):
     def p_sample_loop(self, shape, context, sample_mode, init=None, eta=0):
         if sample_mode != "ddim":
             return self.p_sample(None, None, context, self.clip_noise, sample_mode, eta)
-        if self.pred_mode != "noise":
-            raise NotImplementedError("the eps engine implements pred_mode='noise'")
         return self._run_loop(shape, context, init, eta, "noise", self._clip_mode(self.clip_noise))
 
     @torch.no_grad()

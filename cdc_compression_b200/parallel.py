@@ -3,7 +3,11 @@
 The path shards naturally: no operator mixes batch elements.  Rank r decodes images
 [lo_r, hi_r) — running ``context_fn`` on its own shard, so no context tensor crosses NVLink — and the
 only collective is one all-gather of the decoded images at the end.  The init noise is drawn for the
-WHOLE batch before the split, so a G-GPU decode is bit-identical per image to the 1-GPU decode.
+WHOLE batch before the split, so a G-GPU decode is bit-identical per image to the 1-GPU decode — for the
+deterministic sampler (eta == 0) and the per-image clip modes ("none" / "full").  Two settings couple the result to
+the shard and are rejected when world_size > 1: eps ``clip_noise="half"`` (the reference clamps the first B/2 images
+of the batch it is given, denoising_diffusion.py:142-143 — of the LOCAL shard here) and ``eta != 0`` (every rank
+would draw its own noise stream).
 """
 from __future__ import annotations
 
@@ -44,6 +48,15 @@ def sharded_decode(decode_fn: Callable[..., Tuple[torch.Tensor, torch.Tensor]], 
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:
         rank, world = 0, 1
+    if world > 1:
+        owner = getattr(getattr(decode_fn, "func", decode_fn), "__self__", None)   # functools.partial(d.compress, ...)
+        eta = kwargs.get("eta", getattr(decode_fn, "keywords", {}).get("eta", 0))
+        if eta:
+            raise NotImplementedError("sharded_decode: eta != 0 draws per-rank noise streams; decode on one rank or "
+                                      "pass eta=0")
+        if getattr(owner, "clip_noise", None) == "half":
+            raise NotImplementedError("sharded_decode: clip_noise='half' clamps the first half of the LOCAL batch; "
+                                      "use 'none' or 'full' when sharding")
     lo, hi = shard_range(n, rank, world)
     if hi > lo:
         x_hat, bpp = decode_fn(images[lo:hi], init=None if init is None else init[lo:hi], **kwargs)

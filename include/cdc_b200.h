@@ -6,10 +6,14 @@
  * Every entry point below names the reference interface it replaces (paths relative to the
  * upstream tree).  Plain pointers and sizes only — no torch types.  All device pointers are
  * owned by the caller (PyTorch allocates inputs, outputs and the workspace); the engine owns
- * only the repacked weights.  Work is enqueued on the caller's stream and never synchronises
- * except on error paths.  Every function returns 0 on success and a negative cdc_status
- * otherwise; cdc_last_error() gives the message.  An engine is not re-entrant across host
- * threads.
+ * only the repacked weights.  The compute entry points (cdc_unet_forward, cdc_set_context,
+ * cdc_set_schedule, cdc_context_decode, cdc_ddim_step, cdc_sample_loop) enqueue their work on the
+ * caller's stream and never synchronise it (cdc_set_schedule stages the table in an engine-owned
+ * pinned buffer and waits only for its OWN previous copy, if that is still in flight; growing the
+ * table re-allocates it); the introspection entry points marked "(synchronises)" do.  Every entry
+ * point leaves the calling thread's current CUDA device as it found it.  Every function returns 0
+ * on success and a negative cdc_status otherwise; cdc_last_error() gives the message.  An engine is
+ * not re-entrant across host threads.
  */
 #ifndef CDC_B200_H_
 #define CDC_B200_H_

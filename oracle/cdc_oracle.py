@@ -66,18 +66,29 @@ def block(sd: StateDict, p: str, x: Tensor) -> Tensor:
     return F.relu(y)
 
 
-def resnet_block(sd: StateDict, p: str, x: Tensor, temb: Optional[Tensor]) -> Tensor:
-    """block1 -> (+ Linear(LeakyReLU_0.2(temb)) broadcast over pixels) -> block2 -> + res_conv(x)."""
+def _tap(taps: Optional[dict], name: str, t: Tensor) -> Tensor:
+    """Record an intermediate under the CUDA engine's op name (per-op parity tests); no effect on the arithmetic."""
+    if taps is not None:
+        taps[name] = t
+    return t
+
+
+def resnet_block(sd: StateDict, p: str, x: Tensor, temb: Optional[Tensor], taps: Optional[dict] = None) -> Tensor:
+    """block1 -> (+ Linear(LeakyReLU_0.2(temb)) broadcast over pixels) -> block2 -> + res_conv(x).
+
+    ``taps`` (optional) receives '<p>block1' = block1 output incl. the timestep shift, '<p>res_conv', and '<p>block2' =
+    the block's output (block2 + residual) — the tensors the engine's launches of the same names store."""
     h = block(sd, p + "block1.", x)
     if temb is not None and (p + "mlp.1.weight") in sd:
         shift = F.linear(F.leaky_relu(temb, 0.2), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])
         h = h + shift[:, :, None, None]
+    _tap(taps, p + "block1", h)
     h = block(sd, p + "block2.", h)
     if (p + "res_conv.weight") in sd:
-        r = F.conv2d(x, sd[p + "res_conv.weight"], sd[p + "res_conv.bias"])
+        r = _tap(taps, p + "res_conv", F.conv2d(x, sd[p + "res_conv.weight"], sd[p + "res_conv.bias"]))
     else:
         r = x
-    return h + r
+    return _tap(taps, p + "block2", h + r)
 
 
 def linear_attention(sd: StateDict, p: str, x: Tensor) -> Tensor:
@@ -149,7 +160,8 @@ def _count(sd: StateDict, prefix: str) -> int:
     return len(idx)
 
 
-def unet_forward(sd: StateDict, x: Tensor, time: Optional[Tensor], context: Sequence[Tensor]) -> Tensor:
+def unet_forward(sd: StateDict, x: Tensor, time: Optional[Tensor], context: Sequence[Tensor],
+                 taps: Optional[dict] = None) -> Tensor:
     """Denoiser forward.  ``sd`` holds the Unet's own keys (no 'denoise_fn.' prefix).
 
     encode: per level  cat([x, context[l]]) if l < len(context) ; RB ; RB ; attn ; push ; downsample
@@ -164,23 +176,23 @@ def unet_forward(sd: StateDict, x: Tensor, time: Optional[Tensor], context: Sequ
         p = f"downs.{l}."
         if l < len(context):
             x = torch.cat([x, context[l]], dim=1)
-        x = resnet_block(sd, p + "0.", x, temb)
-        x = resnet_block(sd, p + "1.", x, temb)
-        x = linear_attention(sd, p + "2.", x)
+        x = resnet_block(sd, p + "0.", x, temb, taps)
+        x = resnet_block(sd, p + "1.", x, temb, taps)
+        x = _tap(taps, p + "2.out", linear_attention(sd, p + "2.", x))
         skips.append(x)
         if (p + "3.conv.weight") in sd:
-            x = downsample(sd, p + "3.", x)
-    x = resnet_block(sd, "mid_block1.", x, temb)
-    x = linear_attention(sd, "mid_attn.", x)
-    x = resnet_block(sd, "mid_block2.", x, temb)
+            x = _tap(taps, p + "3.down", downsample(sd, p + "3.", x))
+    x = resnet_block(sd, "mid_block1.", x, temb, taps)
+    x = _tap(taps, "mid_attn.out", linear_attention(sd, "mid_attn.", x))
+    x = resnet_block(sd, "mid_block2.", x, temb, taps)
     for l in range(n_up):
         p = f"ups.{l}."
         x = torch.cat([x, skips.pop()], dim=1)
-        x = resnet_block(sd, p + "0.", x, temb)
-        x = resnet_block(sd, p + "1.", x, temb)
-        x = linear_attention(sd, p + "2.", x)
+        x = resnet_block(sd, p + "0.", x, temb, taps)
+        x = resnet_block(sd, p + "1.", x, temb, taps)
+        x = _tap(taps, p + "2.out", linear_attention(sd, p + "2.", x))
         if (p + "3.conv.weight") in sd:
-            x = upsample(sd, p + "3.", x)
+            x = _tap(taps, p + "3.up", upsample(sd, p + "3.", x))
     x = layer_norm(x, sd["final_conv.0.g"], sd["final_conv.0.b"])
     return F.conv2d(x, sd["final_conv.1.weight"], sd["final_conv.1.bias"], padding=3)
 
@@ -285,9 +297,19 @@ def ddim_update_eps(sch: SampleSchedule, i: int, x: Tensor, noise: Tensor, clip:
 
 
 def ddim_update_x(sch: SampleSchedule, i: int, x: Tensor, fx: Tensor, clip: bool = True,
-                  eta: float = 0.0, z: Optional[Tensor] = None) -> Tensor:
-    x0 = fx.clamp(-1.0, 1.0) if clip else fx
-    noise = (sch.sqrt_recip_alphas_cumprod[i] * x - x0) / sch.sqrt_recipm1_alphas_cumprod[i]
+                  eta: float = 0.0, z: Optional[Tensor] = None, pred_mode: str = "x") -> Tensor:
+    """xparam/modules/denoising_diffusion.py:152-174; pred_mode "noise" / "v" branches :157-165 (+ :110-114, :130-139)."""
+    if pred_mode == "noise":
+        x0 = sch.sqrt_recip_alphas_cumprod[i] * x - sch.sqrt_recipm1_alphas_cumprod[i] * fx
+    elif pred_mode == "v":
+        x0 = torch.sqrt(sch.alphas_cumprod[i]) * x - torch.sqrt(1.0 - sch.alphas_cumprod[i]) * fx
+    else:
+        x0 = fx
+    x0 = x0.clamp(-1.0, 1.0) if clip else x0
+    if pred_mode == "noise":
+        noise = fx
+    else:
+        noise = (sch.sqrt_recip_alphas_cumprod[i] * x - x0) / sch.sqrt_recipm1_alphas_cumprod[i]
     out = sch.sqrt_alphas_cumprod_prev[i] * x0 + torch.sqrt(
         (sch.one_minus_alphas_cumprod_prev[i] - (eta * sch.sigma[i]) ** 2).clamp(min=0)) * noise
     if eta != 0 and z is not None:
@@ -297,7 +319,7 @@ def ddim_update_x(sch: SampleSchedule, i: int, x: Tensor, fx: Tensor, clip: bool
 
 def sample_loop(sd_unet: StateDict, sch: SampleSchedule, variant: str, context: Sequence[Tensor],
                 init: Tensor, clip=None, steps: Optional[Sequence[int]] = None,
-                unet=unet_forward) -> Tensor:
+                unet=unet_forward, pred_mode: str = "x") -> Tensor:
     """Reversed loop over the S schedule entries (``steps`` restricts it, for bounded timing)."""
     x = init
     order = list(reversed(range(sch.sample_steps))) if steps is None else list(steps)
@@ -307,7 +329,7 @@ def sample_loop(sd_unet: StateDict, sch: SampleSchedule, variant: str, context: 
         if variant == "eps":
             x = ddim_update_eps(sch, i, x, f, clip="none" if clip is None else clip)
         else:
-            x = ddim_update_x(sch, i, x, f, clip=True if clip is None else clip)
+            x = ddim_update_x(sch, i, x, f, clip=True if clip is None else clip, pred_mode=pred_mode)
     return x
 
 

@@ -36,6 +36,22 @@ LOOPS = [  # name, variant, B, H, W, S, seed
     ("eps_loop_s6", "eps", 2, 64, 64, 6, 0),
     ("x_loop_s5", "x", 2, 64, 64, 5, 0),
 ]
+# round 2: the benchmarked geometries (BASELINE.json configs 1-4: 256x256 tiles of 16x8 pixels, 512x768 = the demo
+# scripts' Kodak input), long trajectories (50-step drift; S=65 = the x demo's default) and the
+# x-variant's other pred_mode branches (xparam/modules/denoising_diffusion.py:157-165)
+BIG_CASES = [  # name, variant, B, H, W, seed, gain
+    ("eps_b1_256x256", "eps", 1, 256, 256, 3, 1.0),
+    ("x_b1_256x256", "x", 1, 256, 256, 3, 1.0),
+    ("eps_b1_512x768", "eps", 1, 512, 768, 4, 1.0),
+]
+LONG_LOOPS = [  # name, variant, B, H, W, S, seed, gain
+    ("eps_loop_s50_smallgain", "eps", 1, 64, 64, 50, 2, 0.5),
+    ("x_loop_s65", "x", 1, 64, 64, 65, 2, 1.0),
+]
+PRED_LOOPS = [  # name, pred_mode, B, H, W, S, seed   (x variant, clip_denoised=True)
+    ("x_noise_s5", "noise", 1, 32, 32, 5, 0),
+    ("x_v_s5", "v", 1, 32, 32, 5, 0),
+]
 
 
 def case_inputs(variant, B, H, W, seed):
@@ -52,6 +68,41 @@ def ctxdec_latent(sd, B, H, W, seed):
     C = sd["context_fn.dec.0.0.block1.block.0.weight"].shape[1]
     g = torch.Generator().manual_seed(11 + seed)
     return (torch.randn(B, C, H // 16, W // 16, generator=g) * 2).round()
+
+
+def main_round2():
+    """Fixtures added in round 2 (the round-1 files above are left untouched)."""
+    torch.set_grad_enabled(False)
+    for name, variant, B, H, W, seed, gain in BIG_CASES:
+        _, diff = build_reference_diffusion(variant, with_context_fn=False)
+        diff.denoise_fn.load_state_dict(O.seeded_unet_state_dict(variant, seed, gain=gain))
+        x, t, ctx, _ = case_inputs(variant, B, H, W, seed)
+        y = diff.denoise_fn(x, t, ctx)
+        np.savez_compressed(os.path.join(HERE, f"unet_{name}.npz"), out=y.numpy().astype(np.float32),
+                            meta=np.array([B, H, W, seed], dtype=np.int64), gain=np.float32(gain))
+        print(name, tuple(y.shape), float(y.abs().mean()))
+    for name, variant, B, H, W, S, seed, gain in LONG_LOOPS:
+        _, diff = build_reference_diffusion(variant, with_context_fn=False)
+        diff.denoise_fn.load_state_dict(O.seeded_unet_state_dict(variant, seed, gain=gain))
+        _, _, ctx, init = case_inputs(variant, B, H, W, seed)
+        diff.set_sample_schedule(S, torch.device("cpu"))
+        if variant == "eps":
+            out = diff.p_sample_loop(init.shape, ctx, "ddim", init=init.clone(), eta=0)
+        else:
+            out = diff.p_sample_loop(init.shape, ctx, clip_denoised=True, init=init.clone(), eta=0)
+        np.savez_compressed(os.path.join(HERE, f"loop_{name}.npz"), out=out.numpy(),
+                            meta=np.array([B, H, W, S, seed], dtype=np.int64), gain=np.float32(gain))
+        print(name, tuple(out.shape), float(out.abs().max()))
+    for name, pred_mode, B, H, W, S, seed in PRED_LOOPS:
+        _, diff = build_reference_diffusion("x", with_context_fn=False)
+        diff.pred_mode = pred_mode
+        diff.denoise_fn.load_state_dict(O.seeded_unet_state_dict("x", seed))
+        _, _, ctx, init = case_inputs("x", B, H, W, seed)
+        diff.set_sample_schedule(S, torch.device("cpu"))
+        out = diff.p_sample_loop(init.shape, ctx, clip_denoised=True, init=init.clone(), eta=0)
+        np.savez_compressed(os.path.join(HERE, f"loop_{name}.npz"), out=out.numpy(),
+                            meta=np.array([B, H, W, S, seed], dtype=np.int64))
+        print(name, tuple(out.shape), float(out.abs().max()))
 
 
 def main():
@@ -99,4 +150,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--round2" in sys.argv:
+        main_round2()
+    else:
+        main()
+        main_round2()

@@ -185,3 +185,42 @@ def test_shard_range_covers_batch():
             spans = [shard_range(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_deepcopy_resets_engine_and_hook_marks_the_copy():
+    """ADVICE r1 (CPU half; the GPU half is tests/test_gpu_parity_r2.py): copy.deepcopy of a drop-in model (what
+    ema_pytorch.EMA does) must not alias the engine handle, and load_state_dict on the copy dirties the copy."""
+    import copy
+    from conftest import build_dropin
+    d = build_dropin("eps", with_context_fn=False)
+    d.denoise_fn._engine = object()          # stands in for a live DenoiserEngine
+    d.denoise_fn._engine_dirty = False
+    c = copy.deepcopy(d)
+    assert c.denoise_fn._engine is None and c.denoise_fn._engine_dirty
+    c.denoise_fn._engine_dirty = False
+    c.load_state_dict(d.state_dict())        # through the parent module, as the demo scripts do
+    assert c.denoise_fn._engine_dirty and not d.denoise_fn._engine_dirty
+    d.denoise_fn._engine = None
+
+
+def test_sharded_decode_rejects_shard_dependent_settings(monkeypatch):
+    import functools
+    import torch.distributed as dist
+    from cdc_compression_b200 import parallel
+
+    class FakeDiffusion:
+        clip_noise = "half"
+
+        def compress(self, images, init=None, **kw):
+            return images, images.flatten(1).sum(1)
+
+    monkeypatch.setattr(dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(dist, "get_rank", lambda group=None: 0)
+    monkeypatch.setattr(dist, "get_world_size", lambda group=None: 2)
+    imgs = torch.zeros(4, 3, 8, 8)
+    with pytest.raises(NotImplementedError, match="half"):
+        parallel.sharded_decode(functools.partial(FakeDiffusion().compress), imgs)
+    ok = FakeDiffusion()
+    ok.clip_noise = "none"
+    with pytest.raises(NotImplementedError, match="eta"):
+        parallel.sharded_decode(ok.compress, imgs, eta=0.5)
