@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py — denoising throughput of the CDC decoder hot path on B200 (and the CPU reference arm).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA engine
-    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # the reference algorithm on host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5|b1]       # our CUDA engine
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]            # the reference algorithm on host cores
 
-Workload (BASELINE.json configs[1]): epsilonparam variant, DDIM sampling loop of a 500-entry schedule,
-batch = 8 images of 256x256 per GPU, eta = 0, clip_noise "none", seeded random-init weights (no checkpoint
-is reachable offline), synthetic inputs.  A "step" is one DDIM step of the whole batch = one U-Net forward
-(143 kernel launches) + the fused eps->x0->x_{t-1} update.  Metric: image-steps/s = images * steps / time
-(pixel-steps/s is the same number x 65536).  Multi-GPU: each rank decodes its own 8 images (batch split,
-no data-path collective) -> weak scaling; the time is the max over ranks of CUDA-event time.
+Default workload = BASELINE.json configs[1] ("--config 2"): epsilonparam variant, DDIM sampling loop of a 500-entry
+schedule, 8 images of 256x256 per GPU, eta = 0, clip_noise "none", seeded random-init weights (no checkpoint is
+reachable offline), synthetic inputs.  A "step" is one DDIM step of the whole batch = one U-Net forward (every launch of
+the plan) + the fused eps->x0->x_{t-1} update.  Metric: image-steps/s = images * steps / time (pixel-steps/s is the same
+number x H*W).  Other BASELINE configs: --config 3 (xparam, 16 x 256x256, 250-entry schedule), 4 (eps, 8 x 512x512 per
+GPU: B=64 over 8 GPUs), 5 (eps, 32 x 256x256), b1 (eps, 1 x 512x768: the demo scripts' per-image call).  The default run
+also times config 4's per-GPU shard for a few steps and reports it under "secondary".
 
-One JSON line is printed by rank 0.  Extra objects: roofline (dominant kernel, measured live with
-CUDA events), cpu_baseline (oracle port on the host cores, bounded sample), e2e (host buffers in/out
-through diffusion.compress()), clocks, gpu_launches, blocks (per-op-family time share).
+Multi-GPU (torchrun, one rank per GPU): the GLOBAL batch (images + init noise for all N ranks) is drawn from one seed,
+rank r decodes images [r*b, (r+1)*b) — weak scaling, `value` has no data-path collective (barrier + max-over-ranks of
+CUDA-event time) — and `e2e` runs the designed sharded path, cdc_compression_b200.parallel.sharded_decode around
+GaussianDiffusion.compress(): pinned host shard -> H2D -> context_fn -> K-step decode -> NCCL all-gather of the decoded
+images -> D2H, everything inside the timed region (the all-gather is also timed on its own).
+
+One JSON line is printed by rank 0.  Extra objects: roofline (dominant kernel, measured live with CUDA events),
+memory_bound (the HBM-graded rows of SURVEY.md 8(d): achieved GB/s and fraction of the measured HBM peak), cpu_baseline
+(oracle port on the host cores, bounded sample), e2e, clocks (NVML, 10 ms period), gpu_launches, blocks.
 """
 from __future__ import annotations
 
@@ -31,9 +38,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-VARIANT = "eps"
-BATCH, HEIGHT, WIDTH, SCHEDULE = 8, 256, 256, 500
-PIX = HEIGHT * WIDTH
+CONFIGS = {   # name -> variant, images per GPU, H, W, schedule entries, BASELINE.json config it is
+    "2": ("eps", 8, 256, 256, 500, "configs[1]"),
+    "3": ("x", 16, 256, 256, 250, "configs[2]"),
+    "4": ("eps", 8, 512, 512, 500, "configs[3] (B=64 over 8 GPUs = 8 per GPU)"),
+    "5": ("eps", 32, 256, 256, 500, "configs[4]"),
+    "b1": ("eps", 1, 512, 768, 200, "the demo scripts' per-image call (test_epsilonparam.py:67-80)"),
+}
+
+
+class Workload:
+    def __init__(self, name):
+        self.name = name
+        self.variant, self.batch, self.H, self.W, self.S, self.what = CONFIGS[name]
+        self.pix = self.H * self.W
+        self.pred, self.clip = ("noise", "none") if self.variant == "eps" else ("x", "full")
+
+    def config(self, workspace_mb=None, n_gpus=1):
+        ws = f"{workspace_mb:.0f} MB workspace" if workspace_mb else "the engine workspace"
+        vname = "epsilonparam" if self.variant == "eps" else "xparam"
+        return {"workload": f"{vname} DDIM decode, {self.S}-entry schedule, batch={self.batch} {self.H}x{self.W} per GPU "
+                            f"(BASELINE.json {self.what}), eta=0, clip={self.clip}, seeded random-init weights",
+                "variant": self.variant, "batch_per_gpu": self.batch, "height": self.H, "width": self.W,
+                "schedule_steps": self.S,
+                "l2_policy": "working set per step (engine workspace of several hundred MB + ~100 MB fp16 weights) "
+                             "exceeds the 126 MB L2; no flush needed"}
 
 
 def load_peaks():
@@ -47,107 +76,147 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons during the timed region: NVML polled every 10 ms from a thread (a 20-step run of
+    ~50 ms still gets samples); falls back to `nvidia-smi -lms 100` when pynvml is unavailable."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.reasons, self.smax = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr, self._proc, self._how = None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = int(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = [(N.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                    (N.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                    (N.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                    (N.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            def pump():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        for bit, name in bits:
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.010)
+            self._thr = threading.Thread(target=pump, daemon=True)
+            self._thr.start()
+            self._how = "nvml, 10 ms period"
+            return
+        except Exception:
+            self._thr = None
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, text=True)
+
+            def pump2():
+                for line in self._proc.stdout:
+                    c = [v.strip() for v in line.split(",")]
+                    try:
+                        self.sm.append(int(float(c[0])))
+                        self.smax = int(float(c[1]))
+                    except (ValueError, IndexError):
+                        continue
+                    for n, v in zip(self.NAMES, c[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            threading.Thread(target=pump2, daemon=True).start()
+            self._how = "nvidia-smi, 100 ms period"
+        except Exception:
+            self._proc = None
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        smax = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=0)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1.0)
+        if self._proc:
+            self._proc.terminate()
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
+                "samples": len(sm), "how": self._how}
 
 
-def build_model(device):
+def build_model(wl, device):
     from conftest import build_dropin
     from oracle import cdc_oracle as O
     torch.manual_seed(0)
-    d = build_dropin(VARIANT)
+    d = build_dropin(wl.variant)
     sd = d.state_dict()
-    for k, v in O.seeded_unet_state_dict(VARIANT, 0, gain=0.5).items():
+    for k, v in O.seeded_unet_state_dict(wl.variant, 0, gain=0.5).items():
         sd["denoise_fn." + k] = v
     d.load_state_dict(sd)
     return d.to(device)
 
 
-def synthetic_batch(seed):
+def synthetic_batch(wl, n_images, seed=100):
+    """Images and init noise of the GLOBAL batch from one seed (drawn before the split across ranks)."""
     g = torch.Generator().manual_seed(seed)
-    images = torch.rand(BATCH, 3, HEIGHT, WIDTH, generator=g) * 2 - 1
-    init = torch.randn(BATCH, 3, HEIGHT, WIDTH, generator=g) * 0.8
+    images = torch.rand(n_images, 3, wl.H, wl.W, generator=g) * 2 - 1
+    init = torch.randn(n_images, 3, wl.H, wl.W, generator=g) * 0.8
     return images, init
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_steps(n_steps, b, hw, warm=1):
-    """Time `n_steps` DDIM steps of a b x 3 x hw x hw batch with the oracle (fp32, all host threads)."""
+def cpu_steps(wl, n_steps, b, h, w, warm=1):
+    """Time `n_steps` DDIM steps of a b x 3 x h x w batch with the oracle (fp32, all host threads)."""
     from oracle import cdc_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = O.seeded_unet_state_dict(VARIANT, 0, gain=0.5)
-    ctx = O.seeded_context(VARIANT, b, hw, hw)
-    sch = O.make_sample_schedule(O.train_alphas_cumprod("linear", 20000), SCHEDULE, VARIANT)
+    sd = O.seeded_unet_state_dict(wl.variant, 0, gain=0.5)
+    ctx = O.seeded_context(wl.variant, b, h, w)
+    T, sched = (20000, "linear") if wl.variant == "eps" else (8193, "cosine")
+    sch = O.make_sample_schedule(O.train_alphas_cumprod(sched, T), wl.S, wl.variant)
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(b, 3, hw, hw, generator=g) * 0.8
+    x = torch.randn(b, 3, h, w, generator=g) * 0.8
     with torch.no_grad():
-        idx = list(range(SCHEDULE - 1, SCHEDULE - 1 - warm, -1))
-        x = O.sample_loop(sd, sch, VARIANT, ctx, x, steps=idx)
+        idx = list(range(wl.S - 1, wl.S - 1 - warm, -1))
+        x = O.sample_loop(sd, sch, wl.variant, ctx, x, steps=idx)
         t0 = time.perf_counter()
-        idx = list(range(SCHEDULE - 1 - warm, SCHEDULE - 1 - warm - n_steps, -1))
-        O.sample_loop(sd, sch, VARIANT, ctx, x, steps=idx)
+        idx = list(range(wl.S - 1 - warm, wl.S - 1 - warm - n_steps, -1))
+        O.sample_loop(sd, sch, wl.variant, ctx, x, steps=idx)
         dt = time.perf_counter() - t0
     return dt
 
 
-def run_reference(args):
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     budget = 150.0
-    t_probe = cpu_steps(1, 1, 64, warm=1)                    # seconds per 64x64 image-step
-    ladder = [(8, 256), (4, 256), (2, 256), (1, 256), (1, 128), (1, 64)]
-    b, hw = ladder[-1]
+    t_probe = cpu_steps(wl, 1, 1, 64, 64, warm=1)                # seconds per 64x64 image-step
+    ladder = [(wl.batch, wl.H, wl.W), (max(1, wl.batch // 2), wl.H, wl.W), (2, wl.H, wl.W), (1, wl.H, wl.W),
+              (1, wl.H // 2, wl.W // 2), (1, 64, 64)]
+    b, h, w = ladder[-1]
     for cand in ladder:
-        est = t_probe * cand[0] * (cand[1] / 64) ** 2 * (args.steps + args.warmup)
+        est = t_probe * cand[0] * (cand[1] * cand[2] / 4096.0) * (args.steps + args.warmup)
         if est <= budget:
-            b, hw = cand
+            b, h, w = cand
             break
-    dt = cpu_steps(args.steps, b, hw, warm=max(1, args.warmup))
-    images_equiv = b * hw * hw / PIX
+    dt = cpu_steps(wl, args.steps, b, h, w, warm=max(1, args.warmup))
+    images_equiv = b * h * w / wl.pix
     value = images_equiv * args.steps / dt
     cores = torch.get_num_threads()
-    sample = f"{args.steps} DDIM steps of a {b}x3x{hw}x{hw} batch (={images_equiv:g} images of 256x256 per step), fp32"
+    sample = (f"{args.steps} DDIM steps of a {b}x3x{h}x{w} batch (={images_equiv:g} images of {wl.H}x{wl.W} per step), fp32, "
+              f"{cores} host threads"
+              + (f"; single-host baseline: at --gpus {args.gpus} this arm still runs on rank 0's host alone" if args.gpus > 1 else ""))
     line = {
         "impl": "reference", "metric": "denoising_image_steps_per_s", "value": value, "unit": "image-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(),
-        "mpix_per_s": value * PIX / 1e6,
+        "config": wl.config(n_gpus=args.gpus),
+        "mpix_per_s": value * wl.pix / 1e6,
         "cpu_baseline": {"value": value, "unit": "image-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "image-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -155,19 +224,78 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(workspace_mb=None):
-    ws = f"{workspace_mb:.0f} MB workspace" if workspace_mb else "the engine workspace (~460 MB)"
-    return {"workload": f"epsilonparam DDIM decode, {SCHEDULE}-entry schedule, batch={BATCH} {HEIGHT}x{WIDTH} per GPU "
-                        "(BASELINE.json configs[1]), eta=0, clip_noise=none, seeded random-init weights",
-            "variant": VARIANT, "batch_per_gpu": BATCH, "height": HEIGHT, "width": WIDTH, "schedule_steps": SCHEDULE,
-            "l2_policy": f"working set per step ({ws} + ~100 MB fp16 weights) exceeds the 126 MB L2; no flush needed"}
-
-
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def time_loop(wl, eng, x, K, Wm, barrier, sampler=None):
+    """W warm-up steps, then exactly K steps between two CUDA events; returns elapsed ms (this rank)."""
+    cursor = [wl.S - 1]
+
+    def run_steps(n):
+        # n consecutive DDIM steps of the schedule; a decode that reaches i = 0 restarts at i = S-1
+        while n > 0:
+            seg = min(n, cursor[0] + 1)
+            eng.sample_loop(x, cursor[0], cursor[0] - seg + 1, wl.pred, wl.clip)
+            cursor[0] -= seg
+            if cursor[0] < 0:
+                cursor[0] = wl.S - 1
+            n -= seg
+
+    run_steps(Wm)                                                  # warm-up (first step eager, graph captured)
+    if sampler:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run_steps(K)
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
+def memory_bound_rows(wl, prof, peaks):
+    """the rows graded on HBM GB/s.  Algorithmic bytes per launch in two conventions: `single` = one fp16
+    copy of every activation (the survey's minimum), `hilo` = what the engine's compensated trunk (fp16 value + fp16
+    remainder) really moves.  dram_bytes = ncu dram__bytes_read+write of the same launches when a committed
+    capture exists (profiles/ncu_traffic_r02.json)."""
+    B, H, W = wl.batch, wl.H, wl.W
+    a0 = B * H * W * 64 * 2                     # one fp16 copy of a 64-channel full-resolution activation
+    xs = B * 3 * H * W * 4                      # sampler state, fp32
+    rows = {
+        "final_conv": (["final_conv"], a0 + 2 * xs, a0 + 2 * xs),
+        "ups.4.3.up": (["ups.4.3.up"], a0 // 4 + a0, 2 * a0 // 4 + a0),
+        "downs.0.3.down": (["downs.0.3.down"], a0 + a0 // 4, 2 * a0 + 2 * a0 // 4),
+        "downs.0.2 attention": (["downs.0.2.ctx", "downs.0.2.combine", "downs.0.2.T", "downs.0.2.M", "downs.0.2.out"],
+                                3 * a0, 6 * a0),
+        "ups.4.2 attention": (["ups.4.2.ctx", "ups.4.2.combine", "ups.4.2.T", "ups.4.2.M", "ups.4.2.out"],
+                              3 * a0 // 4, 6 * a0 // 4),
+        "pack_input": (["pack_input"], xs + a0, xs + a0),
+    }
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as f:
+            traffic = json.load(f).get("memory_bound", {})
+    except Exception:
+        pass
+    ms_of = {}
+    for n, m, _ in prof:
+        ms_of[n.replace("#partials", "")] = ms_of.get(n.replace("#partials", ""), 0.0) + m
+    out = {}
+    for name, (ops, single, hilo) in rows.items():
+        ms = sum(ms_of.get(o, 0.0) for o in ops)
+        if ms <= 0:
+            continue
+        out[name] = {"ms": ms, "bytes_single_fp16": single, "bytes_hi_lo": hilo,
+                     "gbs_single_fp16": single / ms / 1e6, "gbs_hi_lo": hilo / ms / 1e6,
+                     "hbm_frac_single_fp16": single / ms / 1e6 / peaks["hbm_gbs"],
+                     "hbm_frac_hi_lo": hilo / ms / 1e6 / peaks["hbm_gbs"],
+                     "dram_bytes_ncu": traffic.get(name)}
+    return {"peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"], "rows": out}
+
+
+def run_ours(args, wl):
     import torch.distributed as dist
+    from cdc_compression_b200 import parallel
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -179,80 +307,107 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     peaks = load_peaks()
     K, Wm = args.steps, args.warmup
+    B, H, W, S = wl.batch, wl.H, wl.W, wl.S
+    G = B * world                                                  # global batch
 
-    model = build_model(device)
-    images, init = synthetic_batch(100 + rank)
-    images_d, init_d = images.to(device), init.to(device)
+    model = build_model(wl, device)
+    images, init = synthetic_batch(wl, G)                          # the GLOBAL batch, one seed, before the split
+    lo, hi = parallel.shard_range(G, rank, world)
+    images_d, init_d = images[lo:hi].to(device), init[lo:hi].to(device)
     with torch.no_grad():
-        ctx = model.context_fn(images_d, None)["output"]
-    model.set_sample_schedule(SCHEDULE, device)
+        ctx = (model.context_fn(images_d, None) if wl.variant == "eps" else model.context_fn(images_d))["output"]
+    model.set_sample_schedule(S, device)
     x = init_d.clone().contiguous()
     eng = model._bind(x, ctx, 0.0)
-    eng.set_context(ctx, BATCH, HEIGHT, WIDTH)
-    flops_step = eng.flops_per_forward(BATCH, HEIGHT, WIDTH)
-    launches_step = eng.launches_per_step(BATCH, HEIGHT, WIDTH)
+    eng.set_context(ctx, B, H, W)
+    flops_step = eng.flops_per_forward(B, H, W)
+    launches_step = eng.launches_per_step(B, H, W)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     # ---- device-resident timing: W warm-up steps, then exactly K steps between CUDA events ----
-    cursor = [SCHEDULE - 1]
-
-    def run_steps(n):
-        # n consecutive DDIM steps of the 500-entry schedule; a decode that reaches i = 0 restarts at i = S-1
-        while n > 0:
-            seg = min(n, cursor[0] + 1)
-            eng.sample_loop(x, cursor[0], cursor[0] - seg + 1, "noise", "none")
-            cursor[0] -= seg
-            if cursor[0] < 0:
-                cursor[0] = SCHEDULE - 1
-            n -= seg
-
-    run_steps(Wm)                                                  # warm-up (first step eager, graph captured)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    run_steps(K)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = time_loop(wl, eng, x, K, Wm, barrier, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = t.item()
-    value = world * BATCH * K / (ms_max / 1e3)
+    ms_max = max_over_ranks(ms)
+    value = G * K / (ms_max / 1e3)
     finite = bool(torch.isfinite(x).all())
 
-    # ---- end to end: host (pinned) images + init -> compress() -> host result, K-step decode ----
+    # ---- end to end: the designed multi-GPU path.  Pinned host GLOBAL batch -> this rank's shard H2D -> context_fn ->
+    # Ke-step decode -> all-gather of the decoded images (NCCL, N > 1) -> D2H of the full batch.
     images_p, init_p = images.pin_memory(), init.pin_memory()
     out_host = torch.empty_like(images_p).pin_memory()
 
-    def e2e_once(steps):
-        a = images_p.to(device, non_blocking=True)
-        b = init_p.to(device, non_blocking=True)
-        out, bpp = model.compress(a, sample_steps=steps, sample_mode="ddim", bpp_return_mean=False, init=b)
-        out_host.copy_(out, non_blocking=True)
-        return bpp
+    def decode_shard(img_h, init=None, steps=None):
+        a = img_h.to(device, non_blocking=True)
+        b = init.to(device, non_blocking=True)
+        if wl.variant == "eps":
+            return model.compress(a, sample_steps=steps, sample_mode="ddim", bpp_return_mean=False, init=b)
+        return model.compress(a, sample_steps=steps, bpp_return_mean=False, init=b)
 
-    Ke = min(K, SCHEDULE)                                          # one decode of Ke steps, host buffers both ends
+    def e2e_once(steps):
+        out, bpp = parallel.sharded_decode(decode_shard, images_p, init=init_p, steps=steps)
+        out_host.copy_(out, non_blocking=True)
+        return out, bpp
+
+    Ke = min(K, S)                                                 # one decode of Ke steps, host buffers both ends
     e2e_once(max(2, min(Wm, 8)))                                   # warm
     barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    e2e_once(Ke)
+    out_full, _ = e2e_once(Ke)
     ev1.record()
     barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * BATCH * Ke / (t.item() / 1e3)
-    h2d = (images_p.numel() + init_p.numel()) * 4 / Ke
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    e2e_value = G * Ke / (e2e_ms / 1e3)
+    gather_ms = None
+    if world > 1:                                                  # the path's one collective, timed on its own
+        shard = out_full[lo:hi].contiguous()
+        parallel.gather_batch(shard, G)
+        barrier()
+        ev0.record()
+        parallel.gather_batch(shard, G)
+        ev1.record()
+        barrier()
+        gather_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    h2d = (images_p[lo:hi].numel() + init_p[lo:hi].numel()) * 4 / Ke
     d2h = out_host.numel() * 4 / Ke
+
+    # ---- secondary: BASELINE config 4's per-GPU shard (8 x 512x512), a few steps, device-resident (default run only) ----
+    secondary = None
+    if wl.name == "2" and not args.no_secondary:
+        try:
+            wl4 = Workload("4")
+            del x
+            torch.cuda.empty_cache()
+            img4, init4 = synthetic_batch(wl4, wl4.batch, seed=200 + rank)
+            i4 = img4.to(device)
+            with torch.no_grad():
+                ctx4 = model.context_fn(i4, None)["output"]
+            x4 = init4.to(device).contiguous()
+            model.set_sample_schedule(S, device)                   # the e2e decode left a Ke-entry schedule on the engine
+            eng = model._bind(x4, ctx4, 0.0)
+            eng.set_context(ctx4, wl4.batch, wl4.H, wl4.W)
+            K4 = max(5, min(K, 30))
+            ms4 = max_over_ranks(time_loop(wl, eng, x4, K4, 3, barrier))
+            f4 = eng.flops_per_forward(wl4.batch, wl4.H, wl4.W)
+            secondary = {"config": wl4.config(n_gpus=world), "steps": K4, "ms_per_step": ms4 / K4,
+                         "value": world * wl4.batch * K4 / (ms4 / 1e3), "unit": "image-steps/s",
+                         "mpix_per_s": world * wl4.batch * K4 * wl4.pix / (ms4 / 1e3) / 1e6,
+                         "step_roofline_frac": f4 * K4 / (ms4 * 1e-3) / 1e12 / peaks["tf_sustained"],
+                         "finite": bool(torch.isfinite(x4).all())}
+            del x4, ctx4, i4
+        except Exception as exc:  # a secondary line never takes the headline down
+            secondary = {"error": repr(exc)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -261,11 +416,11 @@ def run_ours(args):
 
     # ---- per-op timing (each op alone, CUDA events) -> dominant kernel + per-block table ----
     torch.cuda.synchronize()
-    model.set_sample_schedule(SCHEDULE, device)
+    model.set_sample_schedule(S, device)
     xs = init_d.clone().contiguous()
     eng = model._bind(xs, ctx, 0.0)
-    eng.set_context(ctx, BATCH, HEIGHT, WIDTH)
-    eng.ddim_step(xs, SCHEDULE - 1, None, "noise", "none")
+    eng.set_context(ctx, B, H, W)
+    eng.ddim_step(xs, S - 1, None, wl.pred, wl.clip)
     prof = eng.profile_ops(iters=5)
     if args.ops_out:
         with open(args.ops_out, "w") as f:
@@ -275,7 +430,7 @@ def run_ours(args):
     fam = {}
     for name, pms, fl in prof:
         base = name.replace("#partials", "")
-        key = ("attention" if base.rsplit(".", 1)[-1] in ("ctx", "combine", "T", "M", "finish", "out") else
+        key = ("attention" if base.rsplit(".", 1)[-1] in ("ctx", "combine", "T", "M", "finish", "out", "algebra") else
                "resample" if (base.endswith(".down") or base.endswith(".up")) else
                "res_conv" if base.endswith("res_conv") else
                "block_conv" if ("block1" in base or "block2" in base) else base)
@@ -283,17 +438,19 @@ def run_ours(args):
         f[0] += pms
         f[1] += fl
     # dominant kernel = igemm_tc_kernel (the tcgen05/TMA implicit-GEMM convolution): every launch of it in one step
-    # (Block convs, res_conv, Down/Upsample; sliced layers include their ln_rows_kernel second half).
     conv_ms = sum(v[0] for k, v in fam.items() if k in ("block_conv", "res_conv", "resample"))
     conv_fl = sum(v[1] for k, v in fam.items() if k in ("block_conv", "res_conv", "resample"))
     conv_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     top = max((p for p in prof if p[2] > 0), key=lambda p: p[2] / max(p[1], 1e-9))
     traffic = None
-    try:   # DRAM bytes per launch of the named instance, from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
-            traffic = json.load(f).get("igemm_tc_kernel")
-    except Exception:
-        pass
+    for fn in ("ncu_traffic_r02.json", "ncu_traffic_r01.json"):
+        try:   # DRAM bytes per launch of the named instance, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                traffic = json.load(f).get("igemm_tc_kernel")
+            if traffic:
+                break
+        except Exception:
+            pass
     roofline = {"bound": "tensor", "achieved": conv_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                 "frac": conv_tf / peaks["tf_burst"], "traffic": traffic, "kernel": "igemm_tc_kernel",
                 "launches_per_step": sum(1 for p in prof if p[2] > 0 and not p[0].endswith(".ctx") and p[0] != "final_conv"),
@@ -306,26 +463,32 @@ def run_ours(args):
         "metric": "denoising_image_steps_per_s", "value": value, "unit": "image-steps/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": workload_config(eng.workspace_bytes(BATCH, HEIGHT, WIDTH) / 1e6),
-        "mpix_per_s": value * PIX / 1e6, "batch_steps_per_s": K / (ms_max / 1e3),
+        "config": wl.config(eng.workspace_bytes(B, H, W) / 1e6, n_gpus=world),
+        "mpix_per_s": value * wl.pix / 1e6, "batch_steps_per_s": K / (ms_max / 1e3),
         "roofline": roofline,
         "step_roofline": {"bound": "tensor", "achieved": step_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                           "frac": step_tf / peaks["tf_sustained"], "flops_per_step": flops_step,
                           "peak_source": peaks["source"] + " sustained (whole step)"},
+        "memory_bound": memory_bound_rows(wl, prof, peaks),
         "blocks": {k: {"ms": v[0], "share": v[0] / tot_ms, "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] else 0.0}
                    for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
         "e2e": {"value": e2e_value, "unit": "image-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": f"pinned host images+init -> H2D -> context_fn -> {K}-step DDIM decode -> D2H, via "
-                        "GaussianDiffusion.compress()"},
-        "gpu_launches": launches_step * K * world, "clocks": clocks, "finite": finite,
+                "ms": e2e_ms, "all_gather_ms": gather_ms,
+                "what": f"pinned host global batch ({G} images) -> this rank's shard H2D -> context_fn -> {Ke}-step DDIM "
+                        "decode -> all-gather of the decoded images (NCCL when N > 1) -> D2H, via "
+                        "parallel.sharded_decode(GaussianDiffusion.compress)"},
+        "gpu_launches": launches_step * K * world, "launches_per_step": launches_step, "clocks": clocks, "finite": finite,
+        "secondary": secondary,
     }
     if not args.no_cpu_baseline and world == 1:
         n_cpu = 3
-        dt = cpu_steps(n_cpu, BATCH, 256, warm=1)
-        line["cpu_baseline"] = {"value": BATCH * n_cpu / dt, "unit": "image-steps/s", "cores": torch.get_num_threads(),
+        dt = cpu_steps(wl, n_cpu, min(B, 8), min(H, 256), min(W, 256), warm=1)
+        eq = min(B, 8) * min(H, 256) * min(W, 256) / wl.pix
+        line["cpu_baseline"] = {"value": eq * n_cpu / dt, "unit": "image-steps/s", "cores": torch.get_num_threads(),
                                 "kind": "port",
-                                "sample": f"{n_cpu} DDIM steps (+1 warm-up) of the same {BATCH}x3x256x256 batch with the "
-                                          f"oracle port, fp32, {torch.get_num_threads()} threads, {dt:.1f} s"}
+                                "sample": f"{n_cpu} DDIM steps (+1 warm-up) of a {min(B, 8)}x3x{min(H, 256)}x{min(W, 256)} "
+                                          f"batch (={eq:g} images of {H}x{W} per step) with the oracle port, fp32, "
+                                          f"{torch.get_num_threads()} threads, {dt:.1f} s"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -337,15 +500,18 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default 2 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short 8 x 512x512 measurement of the default run")
     ap.add_argument("--ops-out", default=None, help="write the per-op timing table (JSON) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    wl = Workload(args.config)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_ours(args)
+        run_ours(args, wl)
 
 
 if __name__ == "__main__":

@@ -41,6 +41,9 @@ _SIGNATURES = {
     "cdc_unet_forward": (C.c_int, [_P, _P, _P, C.POINTER(_P), C.c_int, _P, C.c_int, C.c_int, C.c_int, _P,
                                    C.c_int64, _P]),
     "cdc_set_context": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P]),
+    "cdc_engine_has_context_decoder": (C.c_int, [_P]),
+    "cdc_context_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P]),
+    "cdc_engine_read_context": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "cdc_set_schedule": (C.c_int, [_P, C.POINTER(CdcStepCoef), C.c_int, _P]),
     "cdc_ddim_step": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                 C.c_int64, _P]),

@@ -6,6 +6,7 @@ xparam/modules/denoising_diffusion.py:49-108, 152-231.
 """
 from __future__ import annotations
 
+import os
 import warnings
 
 import numpy as np
@@ -122,8 +123,17 @@ class DiffusionBase(nn.Module):
             self._coef_token = object()      # identity of this table: what an engine remembers having received
         return self._coef_cpu
 
-    def _bind(self, x, context, eta):
-        eng = self.denoise_fn.engine_for(x.device)
+    def _context_decoder_source(self):
+        """(version key, state-dict callable) of ``context_fn.dec`` when the engine can run it:
+        hyperprior compressors built with vbr=False.  CDC_CTX_ENGINE=0 keeps the PyTorch decoder (A/B measurements)."""
+        cf = self.context_fn
+        if cf is None or not hasattr(cf, "dec") or getattr(cf, "vbr", False) or os.environ.get("CDC_CTX_ENGINE", "1") == "0":
+            return None
+        key = tuple((p.data_ptr(), p._version) for p in cf.dec.parameters())
+        return key, (lambda: {"context_fn.dec." + k: v for k, v in cf.dec.state_dict().items()})
+
+    def _bind(self, x, context, eta, ctxdec=None):
+        eng = self.denoise_fn.engine_for(x.device, context_decoder=ctxdec)
         coefs = self._coef_table(eta)
         # the engine (not this object) remembers which table it holds: two GaussianDiffusion objects sharing one Unet
         # can then never leave the other's schedule on the engine
@@ -147,13 +157,16 @@ class DiffusionBase(nn.Module):
             for _ in range(steps):
                 torch.randn_like(x)
 
-    def _run_loop(self, shape, context, init, eta, pred_mode, clip_mode):
+    def _run_loop(self, shape, context, init, eta, pred_mode, clip_mode, q_latent=None, ctxdec=None):
         device = self.alphas_cumprod.device
         x = torch.zeros(shape, device=device) if init is None else init.detach().clone()
         x = x.to(torch.float32).contiguous()
-        eng = self._bind(x, context, eta)
+        eng = self._bind(x, context, eta, ctxdec)
         B, _, H, W = x.shape
-        eng.set_context(context, B, H, W)
+        if q_latent is not None:
+            eng.context_decode(q_latent, B, H, W)      # context_fn.decode on the engine, maps stay in the workspace
+        else:
+            eng.set_context(context, B, H, W)
         S = self.sample_steps
         if eta == 0:
             eng.sample_loop(x, S - 1, 0, pred_mode, clip_mode)
@@ -179,6 +192,17 @@ class DiffusionBase(nn.Module):
         z = torch.randn_like(out)
         eng.ddim_step(out, i, z if eta != 0 else None, pred_mode, clip_mode)
         return out
+
+    def _encode_for_decode(self, images, cond=None):
+        """Split of ``context_fn(images)`` for compress(): encoder + entropy model in PyTorch (north_star: "the AE/entropy
+        path"), decoder on the engine.  Returns (q_latent, bpp, decoder source) or None when the engine cannot run the
+        decoder (then compress() calls context_fn as the reference does)."""
+        src = self._context_decoder_source()
+        if src is None or not images.is_cuda:
+            return None
+        cf = self.context_fn
+        q_latent, _, state = cf.encode(images, cond)
+        return q_latent, cf.bpp(images.shape, state), src
 
     def forward(self, images):
         raise NotImplementedError("training (p_losses / forward) is outside the B200 decoder hot path; see DESIGN.md")

@@ -75,6 +75,8 @@ class UnetBase(nn.Module):
         state = self.__dict__.copy()
         state["_engine"] = None
         state["_engine_dirty"] = True
+        state.pop("_ctxdec_key", None)      # closes over the ORIGINAL's context_fn
+        state.pop("_ctxdec_fn", None)
         return state
 
     # ---- engine lifecycle -------------------------------------------------------------------
@@ -86,7 +88,10 @@ class UnetBase(nn.Module):
         """Call after editing parameters in place (load_state_dict / .to() are tracked automatically)."""
         self._engine_dirty = True
 
-    def engine_for(self, device) -> DenoiserEngine:
+    def engine_for(self, device, context_decoder=None) -> DenoiserEngine:
+        """``context_decoder`` = (version key, callable returning the 'context_fn.dec.*' state entries) from the owning
+        GaussianDiffusion: the engine then also runs ``context_fn.decode``.  Sticky: callers that pass None keep whatever
+        decoder the engine already holds."""
         device = torch.device(device)
         if device.type != "cuda":
             raise EngineError("Unet.forward runs on the CUDA engine only (sm_100a); move the module and its "
@@ -106,8 +111,13 @@ class UnetBase(nn.Module):
             self._engine = DenoiserEngine(self.variant, c["dim"], c["dim_mults"], c["context_dim_mults"],
                                           c["channels"], c["context_channels"], device)
             self._engine_dirty = True
+        if context_decoder is not None and context_decoder[0] != getattr(self, "_ctxdec_key", None):
+            self._engine_dirty = True
         if self._engine_dirty:
-            self._engine.load_weights(self.state_dict())
+            if context_decoder is not None:
+                self._ctxdec_key, self._ctxdec_fn = context_decoder
+            fn = getattr(self, "_ctxdec_fn", None)
+            self._engine.load_weights(self.state_dict(), fn() if fn is not None else None)
             self._engine_dirty = False
         return self._engine
 

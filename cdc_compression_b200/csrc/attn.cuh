@@ -370,10 +370,11 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
 // ~2^-21, i.e. fp32-grade — a single fp16 pass here costs 1e-4 on the U-Net output).  m16n8k16 fp16 MMAs: half the
 // instruction count of a 3xTF32 (m16n8k8) form (measured: 25 -> 19 us at C = 384; the legacy mma.sync rate bounds it).
 // These are the per-image C x C products behind M_b = W_out ctx^T (C^-1/2 W_q).
-// 64 x 64 tile per CTA, 4 warps of 32 x 32, K slabs of 32 in a 3-stage cp.async ring.
+// 64 x 64 tile per CTA, 4 warps of 32 x 32, K slabs of 64 in a 3-stage cp.async ring (102 KB: two CTAs per SM).
 struct Gemm3xSmem {
   static constexpr int kLD = 68;      // padded row (floats): the k-pair fragment loads hit 32 distinct banks
-  static constexpr int kSlab = 32;    // K per pipeline stage (K % 32 == 0: C is a multiple of 64)
+  static constexpr int kSlab = 64;    // K per pipeline stage (K % 64 == 0: C is a multiple of 64); 2 x 35 KB in flight per
+                                      // CTA — the loop is load-latency bound (round 1: 32-wide slabs, 17 us at C = 384)
   static constexpr int kStages = 3;
   static constexpr int kBytes = 2 * kStages * kSlab * kLD * 4;
 };

@@ -83,7 +83,8 @@ struct Level {
 };
 
 // ---------------------------------------------------------------- plan
-enum OpKind { OP_PACK, OP_CONV, OP_TIME, OP_ATTN_CTX, OP_COMBINE, OP_SGEMM, OP_FINISH, OP_FINAL, OP_ADVANCE, OP_LNROWS };
+enum OpKind { OP_PACK, OP_CONV, OP_TIME, OP_ATTN_CTX, OP_COMBINE, OP_SGEMM, OP_FINISH, OP_FINAL, OP_ADVANCE, OP_LNROWS,
+              OP_LATENT, OP_UPSMALL };
 
 struct Op {
   int kind = 0;
@@ -111,6 +112,9 @@ struct Op {
   int lane = 0;
   bool join_before = false;
   LnRowsParams lnr{};   // OP_LNROWS: second half of a sliced convolution
+  UpSmallParams ups{};  // OP_UPSMALL: last Upsample of the eps context decoder (C_out <= 8, fp32 NCHW output)
+  struct { __half *hi, *lo; int C, HW; } lat{};   // OP_LATENT: quantised latent fp32 NCHW -> NHWC hi + lo
+  long long ctr_index = -1;   // K-split convolution with the fused finish: first of its 2 x tiles arrival counters
   // debug view of the op's fp16 NHWC output (if any)
   const __half* dbg = nullptr;
   int dC = 0, dH = 0, dW = 0;
@@ -172,12 +176,15 @@ struct Plan {
   uint8_t* ws = nullptr;
   size_t total_bytes = 0;
   std::vector<Op> ops;
+  std::vector<Op> ctx_ops;         // context_fn.decode: latent -> the four context maps of the persistent region
   // persistent region
   std::vector<size_t> ctx_off;     // fp16 NHWC context per level (level 0 of the eps variant: fp32 NCHW copy)
   size_t shifts_off = 0;
   size_t xstate_off = 0;           // fp32 NCHW sampler state the captured graph works on
   size_t raw_off = 0, raw_bytes = 0;   // fp32 partial tiles of the sliced convolutions (after the arena)
   size_t raw2_off = 0, raw2_bytes = 0; // same, for side-lane ops (they overlap main-lane sliced convolutions)
+  size_t ctr_off = 0;                  // per-tile arrival / departure counters of the K-split convolutions (fused finish)
+  long long ctr_count = 0;
   int pack_op = -1, time_op = -1, final_op = -1;
   double flops = 0;
   // captured step graph
@@ -193,6 +200,7 @@ struct RunArgs {
   float* out = nullptr;         // mode 0
   float* x_inout = nullptr;     // mode 1
   const float* z = nullptr;
+  const float* latent = nullptr;   // context decode: quantised latent, fp32 NCHW
   int mode = 0, pred = 0, clip = 0;
   bool advance = false;
 };
@@ -221,7 +229,11 @@ struct cdc_engine {
   bool fuse_res = true;   // res_conv folded into block2 (second TMEM accumulator); CDC_FUSE_RES=0: separate launch
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
   bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
+  bool fuse_lnrows = false;  // CDC_FUSE_LNROWS=1: K-split convolutions finish their rows in the same launch (per-tile arrival counters)
+                             // instead of ln_rows_kernel.  Measured (B=8 256x256): 16 launches fewer but 2.653 vs 2.633 ms/step —
+                             // fence + arrival atomics + the wait for the tile's slowest unit cost what the launch did; off.
   int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
+  int pdl_mode = 1;                         // CDC_PDL: programmatic dependent launch policy (see pdl_for)
   // derived structure
   std::vector<int> dims, cdims;
   bool fold_ctx0 = false;  // small level-0 context folded into the packed input (eps demo)
@@ -233,6 +245,14 @@ struct cdc_engine {
   std::vector<Level> downs, ups;
   ResW mid1, mid2;
   AttnW mid_attn;
+  struct CtxStage {          // context_fn.dec.i = [ResnetBlock (no time embedding), (Identity), Upsample(C_mid -> C_out)]
+    ResW rb;
+    ConvW up;
+    int cin = 0, cmid = 0, cout = 0;
+    bool small_up = false;   // C_out <= 8: fp32 SIMT kernel, weights [ky][kx][c][o] at up_w32
+    size_t up_w32 = 0, up_b32 = 0;
+  };
+  std::vector<CtxStage> ctxdec;
   size_t t_w1 = 0, t_b1 = 0, t_w2 = 0, t_b2 = 0, t_wcat = 0, t_bcat = 0;
   size_t f_g = 0, f_b = 0, f_w = 0, f_bias = 0;
   // plans
@@ -458,6 +478,10 @@ int pack_resnet(cdc_engine* e, const std::string& p, int cin, int cout, int k1,
   if (out->has_res) {
     if ((rc = pack_conv(e, p + "res_conv", cout, cin, 1, 1, segs_res, true, &out->res))) return rc;
   }
+  if (!wcat) {   // ResnetBlock built without a time embedding (context decoder): no shift
+    out->shift_off = -1;
+    return 0;
+  }
   const int dim = e->cfg.dim;
   const HostTensor* mw = find(e, p + "mlp.1.weight", {cout, dim}, &rc);
   if (!mw) return rc;
@@ -466,6 +490,64 @@ int pack_resnet(cdc_engine* e, const std::string& p, int cin, int cout, int k1,
   out->shift_off = (int)bcat->size();
   wcat->insert(wcat->end(), mw->data.begin(), mw->data.end());
   bcat->insert(bcat->end(), mb->data.begin(), mb->data.end());
+  return 0;
+}
+
+// context_fn.dec.* (BigCompressor / ResnetCompressor decoder, epsilonparam/modules/compress_modules.py:144-156,
+// xparam/modules/compress_modules.py:142-151): optional — packed when the keys were registered.
+int pack_context_decoder(cdc_engine* e) {
+  e->ctxdec.clear();
+  const std::string pre = "context_fn.dec.";
+  int n = 0;
+  while (e->weights.count(pre + std::to_string(n) + ".0.block1.block.0.weight")) ++n;
+  if (n == 0) return 0;
+  const cdc_config& cfg = e->cfg;
+  if (n != cfg.n_context)
+    return fail(e, CDC_ERR_UNSUPPORTED, "context decoder has %d stages, the Unet consumes %d context maps", n, cfg.n_context);
+  for (int i = 0; i < n; ++i) {
+    const std::string p = pre + std::to_string(i) + ".";
+    if (e->weights.count(p + "1.scale.weight"))
+      return fail(e, CDC_ERR_UNSUPPORTED, "context decoder with VBRCondition (vbr=True) is not implemented by the engine");
+    cdc_engine::CtxStage st;
+    const HostTensor& w1 = e->weights[p + "0.block1.block.0.weight"];
+    if (w1.shape.size() != 4 || w1.shape[2] != 3) return fail(e, CDC_ERR_UNSUPPORTED, "unexpected shape of %s0.block1", p.c_str());
+    st.cmid = (int)w1.shape[0];
+    st.cin = (int)w1.shape[1];
+    const std::string upk = e->weights.count(p + "2.conv.weight") ? p + "2.conv" : p + "1.conv";
+    auto it = e->weights.find(upk + ".weight");
+    if (it == e->weights.end()) return fail(e, CDC_ERR_MISSING, "missing weight '%s.weight'", upk.c_str());
+    if (it->second.shape.size() != 4 || it->second.shape[0] != st.cmid || it->second.shape[2] != 4)
+      return fail(e, CDC_ERR_MISSING, "weight '%s.weight' has an unexpected shape", upk.c_str());
+    st.cout = (int)it->second.shape[1];
+    const int level = n - 1 - i;   // stage 0 produces the coarsest map
+    if (st.cout != e->cdims[level])
+      return fail(e, CDC_ERR_UNSUPPORTED, "context decoder stage %d produces %d channels, the Unet expects %d at level %d", i,
+                  st.cout, e->cdims[level], level);
+    if (st.cin % 64 || st.cmid % 64 || st.cin > 384 || st.cmid > 384)
+      return fail(e, CDC_ERR_UNSUPPORTED, "context decoder widths %d -> %d unsupported (multiples of 64, <= 384)", st.cin, st.cmid);
+    int rc;
+    std::vector<SegSpec> s1 = {{st.cin, 3, 3, 0, 0, 0}}, sr = {{st.cin, 1, 1, 0, 0, 0}};
+    if ((rc = pack_resnet(e, p + "0.", st.cin, st.cmid, 3, s1, sr, {true}, &st.rb, nullptr, nullptr))) return rc;
+    if (st.cout % 64 == 0) {
+      if ((rc = pack_convT(e, upk, st.cmid, st.cout, &st.up))) return rc;
+    } else if (st.cout <= 8 && level == 0 && e->fold_ctx0) {
+      const HostTensor& w = it->second;
+      const HostTensor* b = find(e, upk + ".bias", {st.cout}, &rc);
+      if (!b) return rc;
+      std::vector<float> w32((size_t)16 * st.cmid * st.cout);
+      for (int c = 0; c < st.cmid; ++c)
+        for (int o = 0; o < st.cout; ++o)
+          for (int ky = 0; ky < 4; ++ky)
+            for (int kx = 0; kx < 4; ++kx)
+              w32[((size_t)(ky * 4 + kx) * st.cmid + c) * st.cout + o] = w.data[(((size_t)c * st.cout + o) * 4 + ky) * 4 + kx];
+      st.small_up = true;
+      st.up_w32 = put_f32(e, w32.data(), w32.size());
+      st.up_b32 = put_f32(e, b->data.data(), b->data.size());
+    } else {
+      return fail(e, CDC_ERR_UNSUPPORTED, "context decoder output width %d at level %d unsupported", st.cout, level);
+    }
+    e->ctxdec.push_back(st);
+  }
   return 0;
 }
 
@@ -516,7 +598,7 @@ int pack_attn(cdc_engine* e, const std::string& p, int C, AttnW* out) {
 }
 
 // ---------------------------------------------------------------- kernel dispatch
-bool g_pdl = false;  // programmatic dependent launch (CDC_PDL=1 enables): measured 2.6 % SLOWER inside the step graph
+bool g_pdl = false;  // set per launch by run_op (pdl_for)
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_kc(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
@@ -745,7 +827,7 @@ struct Builder {
       Op& op = conv(name + "block1", segs1, w.b1.conv, EPI_LN_SHIFT, h1, 1, 0);
       op.conv.ln_g = dptr<float>(e, w.b1.g);
       op.conv.ln_b = dptr<float>(e, w.b1.b);
-      op.conv.shift = ws<float>(pl->shifts_off) + w.shift_off;
+      op.conv.shift = w.shift_off >= 0 ? ws<float>(pl->shifts_off) + w.shift_off : nullptr;
       op.conv.shift_stride = e->R;
     }
     Act out = new_act(w.cout, h, wd, true);
@@ -1169,6 +1251,14 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op, bool allow_dual = true) {
   if (fused)   // whole tiles per pass: the grid is a multiple of n_slices, so blockIdx % n_slices is the CTA's column slice
     op.tc_grid = std::min(tiles_total, std::max(1, (e->num_sms * ctas_per_sm) / t.n_slices)) * t.n_slices;
   if (sliceable && !fused) {
+    // Fused finish (per-tile arrival counters, igemm_tc.cuh): main-lane launches only.  A CTA waits for its tile's other
+    // units, so every CTA of the launch must become resident: the grid never exceeds the SM slots, and the side lane's
+    // concurrent launch keeps the separate ln_rows_kernel (two spinning launches could starve each other of SM slots).
+    if (e->fuse_lnrows && op.lane == 0) {
+      t.fin_epi = op.epi;
+      op.ctr_index = pl->ctr_count;
+      pl->ctr_count += 2ll * tiles_total;
+    }
     const long long out_pix = (long long)B * c.out_H * c.out_W;
     t.raw_split_stride = out_pix * N;
     const size_t need = (size_t)t.k_splits * (size_t)out_pix * (size_t)N * 4;
@@ -1281,6 +1371,7 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
   const cdc_config& cfg = e->cfg;
   const int L = cfg.n_levels;
   pl->B = B; pl->H = H; pl->W = W; pl->ws = wsp;
+  pl->ctr_count = 0;
   Builder bd{e, pl};
   bd.B = B; bd.H = H; bd.W = W;
   bd.arena.no_reuse = e->debug_no_reuse;
@@ -1297,6 +1388,68 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
   pl->shifts_off = take((size_t)B * e->R * 4);
   pl->xstate_off = take((size_t)B * cfg.channels * H * W * 4);
   bd.arena_base = off;
+
+  // ---- context_fn.decode (optional): latent -> [ResnetBlock -> Upsample] x n, each Upsample output IS a context map of
+  // the persistent region (fp16 NHWC, no conversion pass); built first so its activations share the arena with the U-Net's
+  pl->ctx_ops.clear();
+  if (!e->ctxdec.empty()) {
+    const int n = (int)e->ctxdec.size();
+    int h = H >> n, w = W >> n;
+    Act x = bd.new_act(e->ctxdec[0].cin, h, w, true);
+    bool x_in_arena = true;
+    {
+      pl->ops.emplace_back();
+      Op& op = pl->ops.back();
+      op.kind = OP_LATENT;
+      op.name = "context_fn.latent";
+      op.lat = {bd.ws<__half>(x.off), bd.ws<__half>(x.off_lo), x.C, h * w};
+      op.dbg = bd.ws<__half>(x.off);
+      op.dC = x.C; op.dH = h; op.dW = w;
+    }
+    auto drop_x = [&](const Act& a, bool whole) {
+      if (whole) bd.drop(a);
+      else if (a.off_lo) bd.arena.release(a.off_lo - bd.arena_base, a.bytes);   // hi lives in the persistent region
+    };
+    for (int i = 0; i < n; ++i) {
+      const cdc_engine::CtxStage& stg = e->ctxdec[i];
+      const int level = n - 1 - i;
+      const std::string p = "context_fn.dec." + std::to_string(i) + ".";
+      std::vector<Builder::SegIn> s1 = {{x, 3, 3, -1, -1}}, sr = {{x, 1, 1, 0, 0}};
+      Act r = bd.resnet(p + "0.", s1, sr, stg.rb, h, w, nullptr);
+      drop_x(x, x_in_arena);
+      if (!stg.small_up) {
+        Act u;
+        u.C = stg.cout; u.H = 2 * h; u.W = 2 * w;
+        u.bytes = (size_t)B * u.H * u.W * u.C * 2;
+        u.off = pl->ctx_off[level];
+        u.off_lo = i < n - 1 ? bd.arena_base + bd.arena.alloc(u.bytes) : 0;   // the next stage's residual path reads hi + lo
+        std::vector<Builder::SegIn> su = {{r, 2, 2, 0, 0}};
+        bd.conv(p + "up", Builder::three_pass_in(su), stg.up, EPI_BIAS, u, 1, 4);
+        bd.drop(r);
+        x = u;
+        x_in_arena = false;
+      } else {
+        pl->ops.emplace_back();
+        Op& op = pl->ops.back();
+        op.kind = OP_UPSMALL;
+        op.name = p + "up";
+        op.ups.in = bd.ws<__half>(r.off);
+        op.ups.in_lo = bd.lo_ptr<__half>(r);
+        op.ups.wt = dptr<float>(e, stg.up_w32);
+        op.ups.bias = dptr<float>(e, stg.up_b32);
+        op.ups.out = bd.ws<float>(pl->ctx_off[level]);
+        op.ups.B = B; op.ups.h = h; op.ups.w = w; op.ups.Cin = stg.cmid; op.ups.Cout = stg.cout;
+        bd.drop(r);
+        x = Act();
+        x_in_arena = false;
+      }
+      h *= 2;
+      w *= 2;
+    }
+    drop_x(x, x_in_arena);
+    pl->ctx_ops.swap(pl->ops);
+    pl->ops.clear();
+  }
 
   // ---- ops ----
   {
@@ -1446,10 +1599,11 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
   if (have_xn) bd.drop(xn);
   pl->raw_off = (bd.arena_base + bd.arena.peak + 255) & ~size_t(255);
   pl->raw_bytes = 0;
-  {
+  pl->raw2_bytes = 0;
+  auto finish_ops = [&](std::vector<Op>& ops) -> int {
     std::vector<Op> ops2;
-    ops2.reserve(pl->ops.size() + 64);
-    for (auto& op : pl->ops) {
+    ops2.reserve(ops.size() + 64);
+    for (auto& op : ops) {
       if (op.kind == OP_ATTN_CTX && op.use_tc) {
         int rc = setup_attn_tc(e, pl, op);
         if (rc) return rc;
@@ -1470,6 +1624,7 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
       int rc = setup_tc(e, pl, op);
       if (rc) return rc;
       if (!(op.use_tc && op.tcp.epi == EPI_RAW)) { ops2.push_back(op); continue; }
+      if (op.ctr_index >= 0) { ops2.push_back(op); continue; }   // finishes its rows itself (TcConvParams::tile_ctr)
       // sliced convolution = raw partial tiles (this op) + row-wise epilogue (next op, keeps the op's name)
       const ConvParams& c = op.conv;
       Op fin;
@@ -1495,7 +1650,13 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
       ops2.push_back(op);
       ops2.push_back(fin);
     }
-    pl->ops.swap(ops2);
+    ops.swap(ops2);
+    return 0;
+  };
+  {
+    int rc = finish_ops(pl->ctx_ops);
+    if (rc) return rc;
+    if ((rc = finish_ops(pl->ops))) return rc;
     for (size_t i = 0; i < pl->ops.size(); ++i) {
       if (pl->ops[i].kind == OP_TIME) pl->time_op = (int)i;
       if (pl->ops[i].kind == OP_PACK) pl->pack_op = (int)i;
@@ -1503,12 +1664,16 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     }
   }
   pl->raw2_off = (pl->raw_off + pl->raw_bytes + 255) & ~size_t(255);
-  for (auto& op : pl->ops) {
-    float* rawp = reinterpret_cast<float*>(pl->ws + (op.lane == 1 ? pl->raw2_off : pl->raw_off));
-    if (op.kind == OP_CONV && op.use_tc && op.tcp.epi == EPI_RAW) op.tcp.raw = rawp;
-    if (op.kind == OP_LNROWS) op.lnr.raw = rawp;
-  }
-  pl->total_bytes = pl->raw2_off + pl->raw2_bytes;
+  pl->ctr_off = (pl->raw2_off + pl->raw2_bytes + 255) & ~size_t(255);
+  for (std::vector<Op>* ops : {&pl->ctx_ops, &pl->ops})
+    for (auto& op : *ops) {
+      float* rawp = reinterpret_cast<float*>(pl->ws + (op.lane == 1 ? pl->raw2_off : pl->raw_off));
+      if (op.kind == OP_CONV && op.use_tc && op.tcp.epi == EPI_RAW) op.tcp.raw = rawp;
+      if (op.kind == OP_LNROWS) op.lnr.raw = rawp;
+      if (op.kind == OP_CONV && op.ctr_index >= 0)
+        op.tcp.tile_ctr = reinterpret_cast<unsigned int*>(pl->ws + pl->ctr_off) + op.ctr_index;
+    }
+  pl->total_bytes = pl->ctr_off + (size_t)pl->ctr_count * sizeof(unsigned int);
   pl->flops = 0;
   for (auto& op : pl->ops) pl->flops += op.flops;
   return 0;
@@ -1543,11 +1708,26 @@ Plan* get_plan(cdc_engine* e, int B, int H, int W, void* ws, int* rc) {
   return raw;
 }
 
-int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st) {
+// Programmatic dependent launch policy (CDC_PDL): 1 = every kernel of the step (default: every kernel issues
+// griddepcontrol.launch_dependents first and griddepcontrol.wait after its prologue — barrier init, TMEM allocation,
+// tensor-map prefetch, constant vectors — so that prologue overlaps the predecessor's tail), 0 = off, 2 = only the
+// thread-block-cluster convolutions, 3 = mode 2 + every small-grid kernel.  Round 2, B=8 256x256: 2.631 (0) / 2.608 (2) /
+// 2.590 (3) / 2.570 (1) ms per step.  (Round 1 measured mode 1 as a loss on a 4.7 ms step; launches were longer then.)
+bool pdl_for(const cdc_engine* e, const Op& op) {
+  if (e->pdl_mode <= 0) return false;
+  if (e->pdl_mode == 1) return true;
+  const bool cluster_conv = op.kind == OP_CONV && op.use_tc && op.tcp.cluster_n > 1;
+  if (e->pdl_mode == 2) return cluster_conv;
+  const bool small = op.kind == OP_SGEMM || op.kind == OP_COMBINE || op.kind == OP_LNROWS || op.kind == OP_FINISH ||
+                     (op.kind == OP_CONV && op.use_tc && op.tc_grid <= e->num_sms);
+  return cluster_conv || small;
+}
+
+int run_op(cdc_engine* e, Plan* pl, const Op& op, size_t i, const RunArgs& a, cudaStream_t st) {
   const cdc_config& cfg = e->cfg;
   const int B = pl->B, H = pl->H, W = pl->W;
   {
-    const Op& op = pl->ops[i];
+    g_pdl = pdl_for(e, op);
     switch (op.kind) {
       case OP_TIME: {
         const size_t sm = (size_t)5 * cfg.dim * 4;
@@ -1636,6 +1816,18 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
         }
         break;
       }
+      case OP_LATENT: {
+        if (!a.latent) return fail(e, CDC_ERR_INVALID, "context decode without a latent");
+        dim3 grid((op.lat.HW + 31) / 32, (op.lat.C + 31) / 32, B);
+        launch_k(nchw_to_nhwc_hilo_kernel, grid, dim3(256), 0, st, a.latent, op.lat.C, op.lat.HW, op.lat.hi, op.lat.lo);
+        break;
+      }
+      case OP_UPSMALL: {
+        const long long total = (long long)op.ups.B * op.ups.h * op.ups.w * 4;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)e->num_sms * 8);
+        launch_k(upsample_small_kernel, dim3(blocks), dim3(256), (size_t)16 * op.ups.Cin * op.ups.Cout * 4, st, op.ups);
+        break;
+      }
       default:
         break;
     }
@@ -1646,10 +1838,10 @@ int run_op(cdc_engine* e, Plan* pl, size_t i, const RunArgs& a, cudaStream_t st)
   return 0;
 }
 
-int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
+int run_ops(cdc_engine* e, Plan* pl, const std::vector<Op>& ops, const RunArgs& a, cudaStream_t st) {
   bool side_busy = false;
-  for (size_t i = 0; i < pl->ops.size(); ++i) {
-    const Op& op = pl->ops[i];
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const Op& op = ops[i];
     cudaStream_t use = st;
     if (op.lane == 1) {
       if (!side_busy) {   // fork: the side lane starts after everything enqueued on the main lane so far
@@ -1663,14 +1855,21 @@ int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
       CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_join, 0));
       side_busy = false;
     }
-    int rc = run_op(e, pl, i, a, use);
+    int rc = run_op(e, pl, op, i, a, use);
     if (rc) return rc;
   }
   if (side_busy) {
     CUDA_TRY(e, cudaEventRecord(e->ev_join, e->side_stream));
     CUDA_TRY(e, cudaStreamWaitEvent(st, e->ev_join, 0));
   }
+  return 0;
+}
+
+int run_plan(cdc_engine* e, Plan* pl, const RunArgs& a, cudaStream_t st) {
+  int rc = run_ops(e, pl, pl->ops, a, st);
+  if (rc) return rc;
   if (a.advance) {
+    g_pdl = e->pdl_mode == 1;
     launch_k(advance_step_kernel, dim3(1), dim3(32), 0, st, e->d_step);
   }
   e->last_plan = pl;
@@ -1682,9 +1881,16 @@ __global__ void set_int_kernel(int* p, int v) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
 }
 
+int reset_counters(cdc_engine* e, Plan* pl, cudaStream_t st) {
+  if (pl->ctr_count > 0)   // arrival counters of the K-split convolutions: zero whenever the workspace is (re)initialised
+    CUDA_TRY(e, cudaMemsetAsync(pl->ws + pl->ctr_off, 0, (size_t)pl->ctr_count * sizeof(unsigned int), st));
+  return 0;
+}
+
 int convert_context(cdc_engine* e, Plan* pl, const float* const* ctx, int n_ctx, cudaStream_t st) {
   const cdc_config& cfg = e->cfg;
   if (n_ctx != cfg.n_context) return fail(e, CDC_ERR_INVALID, "expected %d context tensors, got %d", cfg.n_context, n_ctx);
+  if (int rc = reset_counters(e, pl, st)) return rc;
   for (int l = 0; l < n_ctx; ++l) {
     const int c = e->cdims[l], h = pl->H >> l, w = pl->W >> l;
     if (!ctx[l]) return fail(e, CDC_ERR_INVALID, "context[%d] is null", l);
@@ -1772,6 +1978,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("CDC_SLICED")) e->sliced = atoi(v) != 0;
   if (const char* v = getenv("CDC_NSLICE")) e->nslice = atoi(v) != 0;
+  if (const char* v = getenv("CDC_FUSE_LNROWS")) e->fuse_lnrows = atoi(v) != 0;
   if (const char* v = getenv("CDC_ATTN_TC")) e->attn_tc = atoi(v) != 0;
   if (const char* v = getenv("CDC_FUSE_RES")) e->fuse_res = atoi(v) != 0;
   if (const char* v = getenv("CDC_DUAL_PASS")) e->dual_pass = atoi(v) != 0;
@@ -1779,7 +1986,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_FOLD_FINISH")) e->fold_finish = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
-  if (const char* v = getenv("CDC_PDL")) g_pdl = atoi(v) != 0;
+  if (const char* v = getenv("CDC_PDL")) e->pdl_mode = atoi(v);
   if (const char* v = getenv("CDC_SLICE_SLOTS")) e->slice_slots = std::max(1, atoi(v));
   if (const char* v = getenv("CDC_SLICE_KMAX")) e->slice_kmax = std::max(1, atoi(v));
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
@@ -1952,6 +2159,7 @@ int cdc_engine_finalize(cdc_engine* e) {
     e->w_ident = e->blob.reserve(ident.size() * 2);
     memcpy(e->blob.at<__half>(e->w_ident), ident.data(), ident.size() * 2);
   }
+  if ((rc = pack_context_decoder(e))) return rc;
   e->R = (int)bcat.size();
   e->t_wcat = put_f32(e, wcat.data(), wcat.size());
   e->t_bcat = put_f32(e, bcat.data(), bcat.size());
@@ -2022,6 +2230,57 @@ int cdc_set_context(cdc_engine* e, const float* const* ctx, int n_ctx, int B, in
   if ((rc = convert_context(e, pl, ctx, n_ctx, (cudaStream_t)stream))) return rc;
   e->ctx_set = true;
   e->ctx_B = B; e->ctx_H = H; e->ctx_W = W; e->ctx_ws = (uintptr_t)workspace;
+  return CDC_OK;
+}
+
+int cdc_engine_has_context_decoder(cdc_engine* e) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!e->finalized) return fail(e, CDC_ERR_STATE, "engine not finalized");
+  return e->ctxdec.empty() ? 0 : 1;
+}
+
+int cdc_context_decode(cdc_engine* e, const float* q_latent, int B, int H, int W, void* workspace, int64_t workspace_bytes,
+                       void* stream) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!workspace || !q_latent) return fail(e, CDC_ERR_INVALID, "null pointer argument");
+  DeviceGuard dg(e->device);
+  int rc;
+  Plan* pl = get_plan(e, B, H, W, workspace, &rc);
+  if (!pl) return rc;
+  if ((rc = check_ws(e, pl, workspace_bytes))) return rc;
+  if (pl->ctx_ops.empty())
+    return fail(e, CDC_ERR_STATE, "no context decoder weights registered (context_fn.dec.* keys before cdc_engine_finalize)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = reset_counters(e, pl, st))) return rc;
+  RunArgs a;
+  a.latent = q_latent;
+  if ((rc = run_ops(e, pl, pl->ctx_ops, a, st))) return rc;
+  e->ctx_set = true;
+  e->ctx_B = B; e->ctx_H = H; e->ctx_W = W; e->ctx_ws = (uintptr_t)workspace;
+  return CDC_OK;
+}
+
+int cdc_engine_read_context(cdc_engine* e, int level, float* out, int B, int H, int W, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  if (!e) return CDC_ERR_INVALID;
+  if (!workspace || !out) return fail(e, CDC_ERR_INVALID, "null pointer argument");
+  DeviceGuard dg(e->device);
+  if (!e->ctx_set || e->ctx_B != B || e->ctx_H != H || e->ctx_W != W || e->ctx_ws != (uintptr_t)workspace)
+    return fail(e, CDC_ERR_STATE, "no context set for this shape and workspace");
+  if (level < 0 || level >= e->cfg.n_context) return fail(e, CDC_ERR_INVALID, "context level %d out of range", level);
+  int rc;
+  Plan* pl = get_plan(e, B, H, W, workspace, &rc);
+  if (!pl) return rc;
+  if ((rc = check_ws(e, pl, workspace_bytes))) return rc;
+  const int c = e->cdims[level], h = H >> level, w = W >> level;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (level == 0 && e->fold_ctx0) {
+    CUDA_TRY(e, cudaMemcpyAsync(out, pl->ws + pl->ctx_off[0], (size_t)B * c * h * w * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    dim3 grid((h * w + 31) / 32, (c + 31) / 32, B);
+    nhwc_half_to_nchw_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(pl->ws + pl->ctx_off[level]), c, h * w, out);
+    CUDA_TRY(e, cudaGetLastError());
+  }
   return CDC_OK;
 }
 
@@ -2209,11 +2468,11 @@ int cdc_engine_profile_ops(cdc_engine* e, int iters, float* ms_out, double* flop
       for (int k = 0; k < 16; ++k) clkbuf[k] = 0;
       pl->ops[i].tcp.dbg_clk = clkbuf;
     }
-    int rc = run_op(e, pl, (size_t)i, args, st);  // warm
+    int rc = run_op(e, pl, pl->ops[i], (size_t)i, args, st);  // warm
     if (rc) return rc;
     CUDA_TRY(e, cudaEventRecord(a, st));
     for (int k = 0; k < iters; ++k)
-      if ((rc = run_op(e, pl, (size_t)i, args, st))) return rc;
+      if ((rc = run_op(e, pl, pl->ops[i], (size_t)i, args, st))) return rc;
     CUDA_TRY(e, cudaEventRecord(b, st));
     CUDA_TRY(e, cudaEventSynchronize(b));
     float ms = 0.f;

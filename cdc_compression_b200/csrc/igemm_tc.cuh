@@ -129,6 +129,14 @@ struct TcConvParams {
   int xchg_stats;            // second exchange for stats_out (row statistics of the stored LayerNorm output)
   float* raw;
   long long raw_split_stride;
+  // Fused finish of the K-split form (tile_ctr != nullptr): after storing its fp32 partial tile a CTA signals the tile's
+  // arrival counter; once all n_slices * k_splits units of the tile have arrived (all CTAs of the launch are co-resident:
+  // the grid never exceeds the SM slots), every unit finishes its share of the tile's rows — K partials summed in a fixed
+  // order, then the fused epilogue `fin_epi` (bias | LayerNorm+ReLU+shift | LayerNorm+ReLU+residual) exactly as
+  // ln_rows_kernel does — so the separate ln_rows_kernel launch disappears.  tile_ctr[2t] = arrivals, [2t+1] = departures;
+  // the last departing unit zeroes both (the counters are launch-invariant, CUDA-graph replays included).
+  unsigned int* tile_ctr;
+  int fin_epi;
 };
 
 constexpr int EPI_RAW = 4;
@@ -415,6 +423,125 @@ __device__ __forceinline__ void pack_out8(const float (&o)[8], uint4& hi, uint4&
   f = unpack_half2(hi.y); lo.y = pack_half2(o[2] - f.x, o[3] - f.y);
   f = unpack_half2(hi.z); lo.z = pack_half2(o[4] - f.x, o[5] - f.y);
   f = unpack_half2(hi.w); lo.w = pack_half2(o[6] - f.x, o[7] - f.y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-wise finish of the K-split ("sliced") form: one warp per output pixel sums the K-split partials (fixed order) and
+// applies the same fused epilogues as the in-kernel path (bias | LayerNorm+ReLU+shift | LayerNorm+ReLU+residual).
+// Runs inside igemm_tc_kernel (fused finish, TcConvParams::tile_ctr) or as ln_rows_kernel (CDC_FUSE_LNROWS=0).
+// ------------------------------------------------------------------------------------------------
+struct LnRowsParams {
+  const float* raw;
+  int k_splits;
+  long long split_stride;
+  int N;
+  long long rows;            // output pixels
+  int pix_per_image;
+  int epi;                   // EPI_BIAS | EPI_LN_SHIFT | EPI_LN_RES
+  const float* bias;
+  const float* ln_g;
+  const float* ln_b;
+  const float* shift;
+  int shift_stride;
+  const __half* res;
+  int res_C0;
+  const __half* res2;
+  const __half* res_lo;
+  const __half* res2_lo;
+  __half* out;
+  __half* out_lo;
+  float2* stats_out;
+  int Ntot;                  // == N (name expected by load_res2)
+};
+
+// One output pixel `pix` of image `img` by one warp.  The partials were written by OTHER SMs during this launch in the
+// fused form: they are read with ld.global.cg (L2), never through L1.
+__device__ __forceinline__ void ln_rows_row(const LnRowsParams& p, long long pix, int img, int lane) {
+  // (Issuing every load of the row up front — bias / gain / offset / shift / residual and eight K partials at a time — was
+  // measured: 188 registers, one block per SM, 8 -> 21 us on the 8192-row Downsample.  The compact form below stays.)
+  const int N = p.N, iters = N >> 6;
+  float2 v[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (i * 32 + lane) * 2;
+    v[i] = (i < iters && p.bias) ? make_float2(p.bias[c], p.bias[c + 1]) : make_float2(0.f, 0.f);
+  }
+  // fixed summation order (deterministic); K partials are fetched four at a time so their latencies overlap
+  for (int k0 = 0; k0 < p.k_splits; k0 += 4) {
+    float2 r[4][6];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float* src = p.raw + (size_t)(k0 + kk) * p.split_stride + (size_t)pix * N;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        r[kk][i] = (i < iters && k0 + kk < p.k_splits) ? __ldcg(reinterpret_cast<const float2*>(src + (i * 32 + lane) * 2))
+                                                       : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        if (i < iters) {
+          v[i].x += r[kk][i].x;
+          v[i].y += r[kk][i].y;
+        }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i < iters) sum += v[i].x + v[i].y;
+  float mean = 0.f, rstd = 1.f;
+  if (p.epi != EPI_BIAS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean = sum / (float)N;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < iters) {
+        const float d0 = v[i].x - mean, d1 = v[i].y - mean;
+        sq += d0 * d0 + d1 * d1;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    rstd = 1.f / sqrtf(sq / (float)N + 1e-5f);
+  }
+  const float* shift = (p.epi == EPI_LN_SHIFT && p.shift) ? p.shift + (size_t)img * p.shift_stride : nullptr;
+  float osum = 0.f, osq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i < iters) {
+      const int c = (i * 32 + lane) * 2;
+      float y0 = v[i].x, y1 = v[i].y;
+      if (p.epi != EPI_BIAS) {
+        y0 = fmaxf((y0 - mean) * rstd * p.ln_g[c] + p.ln_b[c], 0.f);
+        y1 = fmaxf((y1 - mean) * rstd * p.ln_g[c + 1] + p.ln_b[c + 1], 0.f);
+      }
+      if (shift) {
+        y0 += shift[c];
+        y1 += shift[c + 1];
+      }
+      if (p.res && p.epi != EPI_LN_SHIFT) {
+        const float2 rr = load_res2(p, pix, c);
+        y0 += rr.x;
+        y1 += rr.y;
+      }
+      const float2 q = unpack_half2(store_out2(p, (size_t)pix * N + c, y0, y1));
+      osum += q.x + q.y;
+      osq += q.x * q.x + q.y * q.y;
+    }
+  if (p.stats_out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      osum += __shfl_xor_sync(0xffffffffu, osum, o);
+      osq += __shfl_xor_sync(0xffffffffu, osq, o);
+    }
+    if (lane == 0) {
+      const float m = osum / (float)N;
+      const float var = fmaxf(osq / (float)N - m * m, 0.f);
+      p.stats_out[pix] = make_float2(m, 1.f / sqrtf(var + 1e-5f));
+    }
+  }
 }
 
 // EPI: fused epilogue (compile-time, prunes the others); OCC: CTAs per SM the register budget is sized for.
@@ -1174,6 +1301,51 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
       if (EPI == EPI_RAW) {
         tc::tc_fence_before();
         tc::mbar_arrive(bar_tempty + 8 * buf);
+        if (p.tile_ctr != nullptr) {
+          // ---- fused finish: signal this unit's partial tile, wait for the tile's other units, finish a share of the rows ----
+          unsigned int* ctr = p.tile_ctr + 2 * t;
+          __threadfence();                                           // this thread's partial stores: visible device-wide
+          asm volatile("bar.sync 1, 128;" ::: "memory");             // ... for all 128 epilogue threads
+          if (threadIdx.x == 64) {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+            unsigned int seen;
+            const long long t0 = clock64();
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+              if (seen < (unsigned)units_per_tile && clock64() - t0 > 6000000000LL) {
+                printf("cdc igemm_tc: tile %d arrival counter stuck at %u of %d (block %d)\n", t, seen, units_per_tile, blockIdx.x);
+                __trap();
+              }
+            } while (seen < (unsigned)units_per_tile);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          __threadfence();
+          LnRowsParams q;
+          q.raw = p.raw; q.k_splits = p.k_splits; q.split_stride = p.raw_split_stride; q.N = p.Ntot; q.Ntot = p.Ntot;
+          q.rows = 0; q.pix_per_image = 0; q.epi = p.fin_epi;
+          q.bias = p.bias; q.ln_g = p.ln_g; q.ln_b = p.ln_b; q.shift = p.shift; q.shift_stride = p.shift_stride;
+          q.res = p.res; q.res_C0 = p.res_C0; q.res2 = p.res2; q.res_lo = p.res_lo; q.res2_lo = p.res2_lo;
+          q.out = p.out; q.out_lo = p.out_lo; q.stats_out = p.stats_out;
+          const int su = u - t * units_per_tile;
+          const int tile_rows = p.TW * p.TH * p.TB;
+          for (int r0 = su * 4 + (warp - 2); r0 < tile_rows; r0 += units_per_tile * 4) {   // warp-uniform
+            const int rx = r0 % p.TW, ry = (r0 / p.TW) % p.TH, rb = r0 / (p.TW * p.TH);
+            const int x2 = tx * p.TW + rx, y2 = ty * p.TH + ry, b2 = tb * p.TB + rb;
+            if (x2 < p.W && y2 < p.H && b2 < p.B) {
+              const long long pix2 = ((long long)b2 * p.out_H + y2 * p.out_sy + py) * p.out_W + x2 * p.out_sx + px;
+              ln_rows_row(q, pix2, b2, lane);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) {
+            const unsigned int old = atomicAdd(ctr + 1, 1u);
+            if (old == (unsigned)units_per_tile - 1u) {   // last unit to leave: nobody waits on this tile any more
+              ctr[0] = 0u;
+              ctr[1] = 0u;
+              __threadfence();
+            }
+          }
+        }
       }
       c_p12 += e1 - e0;
       c_p3 += CDC_CLK() - e1;
@@ -1195,124 +1367,14 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Second half of the sliced mode: one warp per output pixel sums the K-split partials (fixed order) and applies
-// the same fused epilogues as the in-kernel path (bias | LayerNorm+ReLU+shift | LayerNorm+ReLU+residual).
-// ------------------------------------------------------------------------------------------------
-struct LnRowsParams {
-  const float* raw;
-  int k_splits;
-  long long split_stride;
-  int N;
-  long long rows;            // output pixels
-  int pix_per_image;
-  int epi;                   // EPI_BIAS | EPI_LN_SHIFT | EPI_LN_RES
-  const float* bias;
-  const float* ln_g;
-  const float* ln_b;
-  const float* shift;
-  int shift_stride;
-  const __half* res;
-  int res_C0;
-  const __half* res2;
-  const __half* res_lo;
-  const __half* res2_lo;
-  __half* out;
-  __half* out_lo;
-  float2* stats_out;
-  int Ntot;                  // == N (name expected by load_res2)
-};
-
+// Second half of the sliced mode as its own launch (CDC_FUSE_LNROWS=0; the default finishes inside igemm_tc_kernel).
 __global__ void __launch_bounds__(256) ln_rows_kernel(const LnRowsParams p) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pix >= p.rows) return;
-  const int N = p.N, iters = N >> 6;
-  float2 v[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const int c = (i * 32 + lane) * 2;
-    v[i] = (i < iters && p.bias) ? make_float2(p.bias[c], p.bias[c + 1]) : make_float2(0.f, 0.f);
-  }
-  // fixed summation order (deterministic); K partials are fetched four at a time so their latencies overlap
-  for (int k0 = 0; k0 < p.k_splits; k0 += 4) {
-    float2 r[4][6];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const float* src = p.raw + (size_t)(k0 + kk) * p.split_stride + (size_t)pix * N;
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-        r[kk][i] = (i < iters && k0 + kk < p.k_splits) ? *reinterpret_cast<const float2*>(src + (i * 32 + lane) * 2)
-                                                       : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-        if (i < iters) {
-          v[i].x += r[kk][i].x;
-          v[i].y += r[kk][i].y;
-        }
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-    if (i < iters) sum += v[i].x + v[i].y;
-  float mean = 0.f, rstd = 1.f;
-  if (p.epi != EPI_BIAS) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    mean = sum / (float)N;
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if (i < iters) {
-        const float d0 = v[i].x - mean, d1 = v[i].y - mean;
-        sq += d0 * d0 + d1 * d1;
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    rstd = 1.f / sqrtf(sq / (float)N + 1e-5f);
-  }
-  const float* shift =
-      (p.epi == EPI_LN_SHIFT && p.shift) ? p.shift + (size_t)(pix / p.pix_per_image) * p.shift_stride : nullptr;
-  float osum = 0.f, osq = 0.f;
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-    if (i < iters) {
-      const int c = (i * 32 + lane) * 2;
-      float y0 = v[i].x, y1 = v[i].y;
-      if (p.epi != EPI_BIAS) {
-        y0 = fmaxf((y0 - mean) * rstd * p.ln_g[c] + p.ln_b[c], 0.f);
-        y1 = fmaxf((y1 - mean) * rstd * p.ln_g[c + 1] + p.ln_b[c + 1], 0.f);
-      }
-      if (shift) {
-        y0 += shift[c];
-        y1 += shift[c + 1];
-      }
-      if (p.res && p.epi != EPI_LN_SHIFT) {
-        const float2 rr = load_res2(p, pix, c);
-        y0 += rr.x;
-        y1 += rr.y;
-      }
-      const float2 q = unpack_half2(store_out2(p, (size_t)pix * N + c, y0, y1));
-      osum += q.x + q.y;
-      osq += q.x * q.x + q.y * q.y;
-    }
-  if (p.stats_out) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      osum += __shfl_xor_sync(0xffffffffu, osum, o);
-      osq += __shfl_xor_sync(0xffffffffu, osq, o);
-    }
-    if (lane == 0) {
-      const float m = osum / (float)N;
-      const float var = fmaxf(osq / (float)N - m * m, 0.f);
-      p.stats_out[pix] = make_float2(m, 1.f / sqrtf(var + 1e-5f));
-    }
-  }
+  ln_rows_row(p, pix, (int)(pix / p.pix_per_image), lane);
 }
 
 }  // namespace cdc

@@ -64,6 +64,109 @@ __global__ void nchw_to_nhwc_half_kernel(const float* __restrict__ in, int C, in
   }
 }
 
+// fp32 NCHW [B,C,HW] -> fp16 NHWC [B,HW,C] value + rounding remainder (the quantised latent entering context_fn.decode:
+// a "trunk" tensor — its 1x1 res_conv runs as three compensated passes)
+__global__ void nchw_to_nhwc_hilo_kernel(const float* __restrict__ in, int C, int HW, __half* __restrict__ out,
+                                         __half* __restrict__ out_lo) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, pp = p0 + tx;
+    tile[j][tx] = (c < C && pp < HW) ? in[((size_t)b * C + c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int pp = p0 + j, c = c0 + tx;
+    if (c < C && pp < HW) {
+      const float v = tile[tx][j];
+      const __half h = __float2half_rn(v);
+      out[((size_t)b * HW + pp) * C + c] = h;
+      out_lo[((size_t)b * HW + pp) * C + c] = __float2half_rn(v - __half2float(h));
+    }
+  }
+}
+
+// fp16 NHWC [B,HW,C] -> fp32 NCHW [B,C,HW]   (read-back of a context map: tests / debugging)
+__global__ void nhwc_half_to_nchw_kernel(const __half* __restrict__ in, int C, int HW, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int pp = p0 + j, c = c0 + tx;
+    tile[j][tx] = (c < C && pp < HW) ? __half2float(in[((size_t)b * HW + pp) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, pp = p0 + tx;
+    if (c < C && pp < HW) out[((size_t)b * C + c) * HW + pp] = tile[tx][j];
+  }
+}
+
+// ConvTranspose2d(C_in, C_out <= 8, 4, stride 2, pad 1) with fp32 weights on a hi+lo NHWC input, fp32 NCHW output: the
+// last Upsample of the eps variant's context decoder (64 -> 3 channels, compress_modules.py:150-156), once per decode.
+// Phase form of SURVEY.md Appendix E: output (oy, ox) with parity (py, px) reads the 2 x 2 inputs (i+ty+py-1, j+tx+px-1)
+// through kernel taps (3-2ty-py, 3-2tx-px).  One thread per output pixel; the weights [ky][kx][c][o] sit in shared memory.
+struct UpSmallParams {
+  const __half* in;      // [B, h, w, Cin]
+  const __half* in_lo;   // may be null
+  const float* wt;       // [4][4][Cin][Cout]
+  const float* bias;     // [Cout]
+  float* out;            // [B, Cout, 2h, 2w]
+  int B, h, w, Cin, Cout;
+};
+__global__ void __launch_bounds__(256) upsample_small_kernel(const UpSmallParams p) {
+  extern __shared__ float ws_[];
+  const int nw = 16 * p.Cin * p.Cout;
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) ws_[i] = p.wt[i];   // weights: constant, may precede the wait
+  pdl_wait();
+  __syncthreads();
+  const int OW = 2 * p.w, OH = 2 * p.h;
+  const long long total = (long long)p.B * OH * OW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % OW);
+    const long long t = idx / OW;
+    const int oy = (int)(t % OH), b = (int)(t / OH);
+    const int py = oy & 1, px = ox & 1, i = oy >> 1, j = ox >> 1;
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = o < p.Cout ? p.bias[o] : 0.f;
+    for (int ty = 0; ty < 2; ++ty) {
+      const int iy = i + ty + py - 1, ky = 3 - 2 * ty - py;
+      if (iy < 0 || iy >= p.h) continue;
+      for (int tx = 0; tx < 2; ++tx) {
+        const int ix = j + tx + px - 1, kx = 3 - 2 * tx - px;
+        if (ix < 0 || ix >= p.w) continue;
+        const size_t base = (((size_t)b * p.h + iy) * p.w + ix) * p.Cin;
+        const float* wk = ws_ + (size_t)(ky * 4 + kx) * p.Cin * p.Cout;
+        for (int c0 = 0; c0 < p.Cin; c0 += 8) {
+          const uint4 vh = *reinterpret_cast<const uint4*>(p.in + base + c0);
+          uint4 vl = make_uint4(0u, 0u, 0u, 0u);
+          if (p.in_lo) vl = *reinterpret_cast<const uint4*>(p.in_lo + base + c0);
+          const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 a = unpack_half2(hh[q]), l = unpack_half2(ll[q]);
+            const float x0 = a.x + l.x, x1 = a.y + l.y;
+            const float* w0 = wk + (size_t)(c0 + 2 * q) * p.Cout;
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+              if (o < p.Cout) acc[o] = fmaf(x1, w0[p.Cout + o], fmaf(x0, w0[o], acc[o]));
+          }
+        }
+      }
+    }
+    const size_t plane = (size_t)OH * OW;
+    for (int o = 0; o < p.Cout; ++o) p.out[((size_t)b * p.Cout + o) * plane + (size_t)oy * OW + ox] = acc[o];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Timestep path: temb = W2 gelu_erf(W1 t + b1) + b2 (unet.py:40), then for every ResnetBlock
 // shift = Wk leaky_relu_0.2(temb) + bk (network_components.py:97-101,110-111).  One CTA per image;

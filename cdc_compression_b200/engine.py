@@ -107,9 +107,14 @@ class DenoiserEngine:
         return self._ws
 
     # ------------------------------------------------------------------ weights
-    def load_weights(self, state_dict: Dict[str, torch.Tensor]):
+    def load_weights(self, state_dict: Dict[str, torch.Tensor],
+                     context_decoder: Optional[Dict[str, torch.Tensor]] = None):
         """``state_dict`` = the Unet's own keys.  fp32 host copies are handed
-        to the engine, which repacks them to its fp16 kernel layouts."""
+        to the engine, which repacks them to its fp16 kernel layouts.  ``context_decoder`` (optional) = the
+        compressor's decoder entries under their GaussianDiffusion keys ('context_fn.dec.<i>....'): enables
+        ``context_decode``."""
+        if context_decoder:
+            state_dict = {**state_dict, **context_decoder}
         for key, t in state_dict.items():
             t = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
             shape = (C.c_int64 * t.dim())(*t.shape)
@@ -213,6 +218,29 @@ class DenoiserEngine:
         arr, keep = self._ctx_array(context, B, H, W)
         self._check(self._lib.cdc_set_context(self._h, arr, len(keep), B, H, W, _ptr(ws), ws.numel(),
                                               self._stream()), "cdc_set_context")
+
+    def has_context_decoder(self) -> bool:
+        return self._check(self._lib.cdc_engine_has_context_decoder(self._h), "cdc_engine_has_context_decoder") == 1
+
+    def context_decode(self, q_latent: torch.Tensor, B, H, W):
+        """``context_fn.decode(q_latent)`` on the engine: the four context maps land in the workspace in the layout
+        the U-Net plan reads (replaces ``set_context(context_fn.decode(q_latent))``)."""
+        if q_latent.device != self.device:
+            raise EngineError("latent on the wrong device")
+        q = q_latent.detach().to(torch.float32).contiguous()
+        if q.dim() != 4 or q.shape[0] != B or q.shape[2] * 16 != H or q.shape[3] * 16 != W:
+            raise EngineError(f"latent has shape {tuple(q.shape)}; expected [B={B}, C, {H // 16}, {W // 16}]")
+        ws = self._workspace(B, H, W)
+        self._check(self._lib.cdc_context_decode(self._h, _ptr(q), B, H, W, _ptr(ws), ws.numel(), self._stream()),
+                    "cdc_context_decode")
+
+    def read_context(self, level: int, B, H, W) -> torch.Tensor:
+        """Context map ``level`` as the engine holds it, as fp32 NCHW (tests)."""
+        ws = self._workspace(B, H, W)
+        out = torch.empty(B, self.context_widths[level], H >> level, W >> level, dtype=torch.float32, device=self.device)
+        self._check(self._lib.cdc_engine_read_context(self._h, int(level), _ptr(out), B, H, W, _ptr(ws), ws.numel(),
+                                                      self._stream()), "cdc_engine_read_context")
+        return out
 
     def set_schedule(self, coefs: torch.Tensor):
         """``coefs``: [S, 8] fp32 CPU tensor, columns as in ``cdc_step_coef``."""

@@ -85,8 +85,15 @@ class GaussianDiffusion(DiffusionBase):
     @torch.no_grad()
     def compress(self, images, sample_steps=None, bitrate_scale=None, sample_mode="ddpm", bpp_return_mean=True,
                  init=None, eta=0):
+        steps = self.num_timesteps if sample_steps is None else sample_steps
+        split = self._encode_for_decode(images, bitrate_scale) if sample_mode == "ddim" else None
+        if split is not None:      # context_fn.decode runs on the engine (no NCHW fp32 context round trip)
+            q_latent, bpp, src = split
+            self.set_sample_schedule(steps, images.device)
+            decoded = self._run_loop(images.shape, None, init, eta, "noise", self._clip_mode(self.clip_noise),
+                                     q_latent=q_latent, ctxdec=src)
+            return decoded, (bpp.mean() if bpp_return_mean else bpp)
         ctx = self.context_fn(images, bitrate_scale)
-        self.set_sample_schedule(self.num_timesteps if sample_steps is None else sample_steps,
-                                 ctx["output"][0].device)
+        self.set_sample_schedule(steps, ctx["output"][0].device)
         decoded = self.p_sample_loop(images.shape, ctx["output"], sample_mode, init=init, eta=eta)
         return decoded, (ctx["bpp"].mean() if bpp_return_mean else ctx["bpp"])

@@ -69,11 +69,17 @@ class GaussianDiffusion(DiffusionBase):
 
     @torch.no_grad()
     def compress(self, images, sample_steps=None, bpp_return_mean=True, init=None, eta=0):
-        ctx = self.context_fn(images)
-        self.set_sample_schedule(self.num_timesteps if sample_steps is None else sample_steps,
-                                 ctx["output"][0].device)
-        bpp = ctx["bpp"].mean() if bpp_return_mean else ctx["bpp"]
         if self.ae_fn is not None:
             raise NotImplementedError("latent-space decoding (ae_fn) is not part of the B200 hot path; the demo "
                                       "configuration uses ae_fn=None")
+        steps = self.num_timesteps if sample_steps is None else sample_steps
+        split = self._encode_for_decode(images)
+        if split is not None:      # context_fn.decode runs on the engine (no NCHW fp32 context round trip)
+            q_latent, bpp, src = split
+            self.set_sample_schedule(steps, images.device)
+            decoded = self._run_loop(images.shape, None, init, eta, self.pred_mode, "full", q_latent=q_latent, ctxdec=src)
+            return decoded, (bpp.mean() if bpp_return_mean else bpp)
+        ctx = self.context_fn(images)
+        self.set_sample_schedule(steps, ctx["output"][0].device)
+        bpp = ctx["bpp"].mean() if bpp_return_mean else ctx["bpp"]
         return self.p_sample_loop(images.shape, ctx["output"], clip_denoised=True, init=init, eta=eta), bpp

@@ -106,6 +106,21 @@ int cdc_unet_forward(cdc_engine* e, const float* x, const float* time, const flo
 int cdc_set_context(cdc_engine* e, const float* const* ctx, int n_ctx, int B, int H, int W,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- context_fn.decode on the engine: BigCompressor.decode
+ * (epsilonparam/modules/compress_modules.py:74-82, layers :144-156) / ResnetCompressor.decode
+ * (xparam/modules/compress_modules.py:68-74, layers :142-151), vbr=False.  Register the decoder's state_dict entries with
+ * cdc_engine_set_weight under their GaussianDiffusion keys ('context_fn.dec.<i>.0.block1.block.0.weight', ...,
+ * 'context_fn.dec.<i>.<1|2>.conv.weight') before cdc_engine_finalize.  q_latent: [B, C_latent, H/16, W/16] fp32 NCHW
+ * (device) — the dequantised latent Compressor.encode returns.  Runs [ResnetBlock (no time embedding) -> Upsample] per
+ * stage and leaves the four maps in the workspace in the layout the U-Net plan consumes: equivalent to cdc_set_context
+ * with context_fn.decode(q_latent), without the NCHW fp32 round trip. */
+int cdc_engine_has_context_decoder(cdc_engine* e);   /* 1 / 0 after finalize */
+int cdc_context_decode(cdc_engine* e, const float* q_latent, int B, int H, int W, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+/* Copy context map `level` (as stored by cdc_set_context / cdc_context_decode) to `out` as fp32 NCHW (device). */
+int cdc_engine_read_context(cdc_engine* e, int level, float* out, int B, int H, int W, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+
 /* ---- GaussianDiffusion.set_sample_schedule tables (see cdc_step_coef) ---- */
 int cdc_set_schedule(cdc_engine* e, const cdc_step_coef* host_coefs, int S, void* stream);
 

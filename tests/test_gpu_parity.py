@@ -339,7 +339,9 @@ KERNEL_FORMS = [("CDC_ATTN_TC", "mma.sync attention-context kernel instead of th
                 ("CDC_FINAL_TC", "mma.sync final convolution instead of the tcgen05 one"),
                 ("CDC_DUAL_PASS", "separate W_hi / W_lo passes instead of one activation load feeding two weight tiles"),
                 ("CDC_FUSE_RES", "separate res_conv launches instead of the second TMEM accumulator in block2"),
-                ("CDC_FINAL_PRELN", "final convolution normalises its own halo instead of reading the last Upsample's LayerNorm-ed copy")]
+                ("CDC_FINAL_PRELN", "final convolution normalises its own halo instead of reading the last Upsample's LayerNorm-ed copy"),
+                ("CDC_PDL", "programmatic dependent launch on every kernel (default) vs plain stream order"),
+                ("CDC_FUSE_LNROWS", "K-split convolutions finish their rows in the launch (arrival counters) vs the separate ln_rows_kernel")]
 
 
 @pytest.mark.parametrize("knob", [k for k, _ in KERNEL_FORMS])

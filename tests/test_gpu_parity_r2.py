@@ -243,3 +243,87 @@ def test_mixed_timesteps_raise():
     d.set_sample_schedule(4, dev())
     with pytest.raises(NotImplementedError):
         d.ddim(init.to(dev()), torch.tensor([1, 3], device=dev()), [c.to(dev()) for c in ctx], "none")
+
+
+# ---- context_fn.decode on the engine -------------------------------------------------------------
+from golden.make_golden import CTXDEC, ctxdec_latent  # noqa: E402
+
+
+def _dropin_with_context(variant, seed):
+    d = build_dropin(variant)
+    d.load_state_dict(O.seeded_fill(d.state_dict(), seed=seed, denoiser_gain=0.5))
+    return d
+
+
+@pytest.mark.parametrize("case", CTXDEC, ids=[c[0] for c in CTXDEC])
+def test_context_decode_on_engine_vs_reference_golden(case):
+    """cdc_context_decode (ResnetBlock without time embedding -> Upsample, four stages, the maps left in the U-Net plan's
+    own layout) vs the maps the UNMODIFIED reference's context_fn.decode produced (tests/golden/ctxdec_*.npz)."""
+    name, variant, B, H, W, seed = case
+    gold = np.load(os.path.join(GOLD, f"ctxdec_{name}.npz"))
+    d = _dropin_with_context(variant, seed)
+    q = ctxdec_latent(d.state_dict(), B, H, W, seed)
+    d.to(dev())
+    eng = d.denoise_fn.engine_for(dev(), context_decoder=d._context_decoder_source())
+    assert eng.has_context_decoder()
+    eng.context_decode(q.to(dev()), B, H, W)
+    for l in range(4):
+        got, ref = eng.read_context(l, B, H, W).cpu(), torch.from_numpy(gold[f"out{l}"])
+        assert got.shape == ref.shape
+        e = rel(got, ref)
+        print(f"\n[parity] context_decode {name} level {l} {tuple(ref.shape)}: rel-L2 {e:.3e}")
+        assert e < REL_L2_OP, (l, e)
+
+
+@pytest.mark.parametrize("variant", ["eps", "x"])
+def test_context_decode_on_engine_vs_fp64_oracle_256(variant):
+    """Same at a benchmarked geometry (2 x 256 x 256: 16x16 latent, full 128-pixel tiles at the upper stages) against the
+    float64 oracle restatement (itself pinned to the reference by tests/test_oracle.py)."""
+    B, H, W, seed = 2, 256, 256, 3
+    d = _dropin_with_context(variant, seed)
+    sd = {k: v.clone() for k, v in d.state_dict().items()}
+    q = ctxdec_latent(sd, B, H, W, seed)
+    ref = O.context_decode({k: v.double() for k, v in sd.items() if k.startswith("context_fn.dec.")}, "context_fn.", q.double())
+    d.to(dev())
+    eng = d.denoise_fn.engine_for(dev(), context_decoder=d._context_decoder_source())
+    eng.context_decode(q.to(dev()), B, H, W)
+    for l in range(4):
+        got = eng.read_context(l, B, H, W).cpu()
+        e = rel(got, ref[l])
+        ring = torch.ones(ref[l].shape[2:], dtype=torch.bool)
+        ring[1:-1, 1:-1] = False
+        e_ring = rel(got[:, :, ring], ref[l][:, :, ring])
+        print(f"\n[parity] context_decode {variant} 256x256 level {l}: rel-L2 {e:.3e} (border ring {e_ring:.3e})")
+        assert e < REL_L2_OP and e_ring < REL_L2_OP, (l, e, e_ring)
+
+
+@pytest.mark.parametrize("variant", ["eps", "x"])
+def test_compress_with_engine_context_decoder_matches_pytorch_decoder(variant):
+    """compress() with context_fn.decode on the engine (default) vs with the PyTorch decoder (CDC_CTX_ENGINE=0): same
+    bpp (the entropy path is untouched) and the same decode up to the context maps' fp16 rounding."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    d = _dropin_with_context(variant, 2)
+    if variant == "eps":
+        d.clip_noise = "full"
+    d.to(dev())
+    g = torch.Generator().manual_seed(3)
+    img = (torch.rand(2, 3, 128, 192, generator=g) * 2 - 1).to(dev())
+    init = (torch.randn(2, 3, 128, 192, generator=g) * 0.8).to(dev())
+    kw = dict(sample_mode="ddim") if variant == "eps" else {}
+    outs = {}
+    old = os.environ.get("CDC_CTX_ENGINE")
+    try:
+        for val in ("1", "0"):
+            os.environ["CDC_CTX_ENGINE"] = val
+            outs[val] = d.compress(img, sample_steps=6, bpp_return_mean=False, init=init, **kw)
+    finally:
+        if old is None:
+            os.environ.pop("CDC_CTX_ENGINE", None)
+        else:
+            os.environ["CDC_CTX_ENGINE"] = old
+    assert torch.allclose(outs["1"][1], outs["0"][1], rtol=1e-5)
+    to01 = lambda v: v.cpu().clamp(-1, 1) / 2 + 0.5
+    psnr = O.batch_psnr(to01(outs["1"][0]), to01(outs["0"][0])).min().item()
+    print(f"\n[parity] compress {variant}: engine vs PyTorch context decoder PSNR {psnr:.1f} dB")
+    assert psnr > 50.0, psnr
