@@ -29,6 +29,8 @@ struct AttnCtxParams {
   float* part_m;        // [B][nchunks][C]
   float* part_s;        // [B][nchunks][C]
   float* ctxn;          // nchunks == 1 only: write ctx / S straight to [B][C][C] (no combine pass); else nullptr
+  __half* ctx16_hi;     // optional (with ctxn): the same matrix as fp16 value + remainder in the MN-blocked operand layout of
+  __half* ctx16_lo;     // attn_alg_tc_kernel: element (d, e) at ((e/64) * C + d) * 64 + e % 64, per image
 };
 
 struct AttnCtxSmem {
@@ -303,8 +305,15 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           const int e = eblk * 64 + we * 16 + nt * 8 + (lane & 3) * 2;
-          *reinterpret_cast<float2*>(dst + (size_t)d * C + e) =
-              make_float2(ctx[mt][nt][2 * h] * inv, ctx[mt][nt][2 * h + 1] * inv);
+          const float v0 = ctx[mt][nt][2 * h] * inv, v1 = ctx[mt][nt][2 * h + 1] * inv;
+          *reinterpret_cast<float2*>(dst + (size_t)d * C + e) = make_float2(v0, v1);
+          if (direct && p.ctx16_hi) {
+            const size_t o16 = (((size_t)b * cb + (e >> 6)) * C + d) * 64 + (e & 63);
+            const uint32_t hv = pack_half2(v0, v1);
+            const float2 hf = unpack_half2(hv);
+            *reinterpret_cast<uint32_t*>(p.ctx16_hi + o16) = hv;
+            *reinterpret_cast<uint32_t*>(p.ctx16_lo + o16) = pack_half2(v0 - hf.x, v1 - hf.y);
+          }
         }
       }
     if (!direct && eblk == 0 && tid < 64) {
@@ -316,34 +325,46 @@ __global__ void __launch_bounds__(256) attn_ctx_kernel(const AttnCtxParams p) {
 }
 
 // ctxn[b][d][e] = sum_c part_ctx[b][c][d][e] * exp(m_c[d]-m[d]) / sum_c part_s[b][c][d]*exp(m_c[d]-m[d])
-// One CTA per (d, image).  Warp 0 turns the (<= 64) per-chunk maxima / sums of row d into normalised chunk weights
+// One CTA per (d, image).  Warp 0 turns the (<= 256) per-chunk maxima / sums of row d into normalised chunk weights
 // (lanes over chunks, shuffle reductions: fixed order, deterministic); every thread then owns columns e and adds the
 // weighted chunk partials in chunk order with four loads in flight.
+constexpr int kCombineMaxChunks = 256;
 __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_ctx,
                                                            const float* __restrict__ part_m,
                                                            const float* __restrict__ part_s, int C, int nchunks,
-                                                           float* __restrict__ ctxn) {
+                                                           float* __restrict__ ctxn, __half* __restrict__ ctx16_hi,
+                                                           __half* __restrict__ ctx16_lo) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float w_s[64];
+  __shared__ float w_s[kCombineMaxChunks];
   const int d = blockIdx.x, b = blockIdx.y;
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     const float* pm = part_m + (size_t)b * nchunks * C + d;
     const float* ps = part_s + (size_t)b * nchunks * C + d;
-    const float m0 = lane < nchunks ? pm[(size_t)lane * C] : -INFINITY;
-    const float m1 = lane + 32 < nchunks ? pm[(size_t)(lane + 32) * C] : -INFINITY;
-    float m = fmaxf(m0, m1);
+    // lane l owns chunks l, l + 32, ... (<= kCombineMaxChunks / 32 each); fixed order, shuffle reductions: deterministic
+    float mv[kCombineMaxChunks / 32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kCombineMaxChunks / 32; ++j) {
+      const int c = lane + 32 * j;
+      mv[j] = c < nchunks ? pm[(size_t)c * C] : -INFINITY;
+      m = fmaxf(m, mv[j]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float w0 = lane < nchunks ? __expf(m0 - m) : 0.f;
-    const float w1 = lane + 32 < nchunks ? __expf(m1 - m) : 0.f;
-    float S = (lane < nchunks ? ps[(size_t)lane * C] * w0 : 0.f) + (lane + 32 < nchunks ? ps[(size_t)(lane + 32) * C] * w1 : 0.f);
+    float S = 0.f;
+#pragma unroll
+    for (int j = 0; j < kCombineMaxChunks / 32; ++j) {
+      const int c = lane + 32 * j;
+      mv[j] = c < nchunks ? __expf(mv[j] - m) : 0.f;
+      S += c < nchunks ? ps[(size_t)c * C] * mv[j] : 0.f;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
     const float inv = 1.f / S;
-    w_s[lane] = w0 * inv;
-    w_s[lane + 32] = w1 * inv;
+#pragma unroll
+    for (int j = 0; j < kCombineMaxChunks / 32; ++j) w_s[lane + 32 * j] = mv[j] * inv;
   }
   __syncthreads();
   const size_t cstride = (size_t)C * C;
@@ -361,6 +382,12 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
     }
     for (; c < nchunks; ++c) a = fmaf(src[(size_t)c * cstride + e], w_s[c], a);
     ctxn[((size_t)b * C + d) * C + e] = a;
+    if (ctx16_hi) {   // operand layout of attn_alg_tc_kernel (see AttnCtxParams::ctx16_hi)
+      const size_t o16 = (((size_t)b * (C >> 6) + (e >> 6)) * C + d) * 64 + (e & 63);
+      const __half hv = __float2half_rn(a);
+      ctx16_hi[o16] = hv;
+      ctx16_lo[o16] = __float2half_rn(a - __half2float(hv));
+    }
   }
 }
 

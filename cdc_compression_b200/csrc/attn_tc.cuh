@@ -40,6 +40,8 @@ struct AttnTcParams {
   float* part_m;            // [B][nchunks][C]
   float* part_s;            // [B][nchunks][C]
   float* ctxn;              // nchunks == 1 only: write ctx / S straight to [B][C][C] (no combine pass); else nullptr
+  __half* ctx16_hi;         // optional (with ctxn): fp16 value + remainder in attn_alg_tc_kernel's MN-blocked operand layout
+  __half* ctx16_lo;
 };
 
 constexpr int kAttnTcThreads = 192;
@@ -351,6 +353,20 @@ attn_ctx_tc_kernel(const __grid_constant__ TcMaps maps, const AttnTcParams p) {
             reinterpret_cast<float4*>(dst + c0)[q] =
                 make_float4(__uint_as_float(t[4 * q]) * inv, __uint_as_float(t[4 * q + 1]) * inv,
                             __uint_as_float(t[4 * q + 2]) * inv, __uint_as_float(t[4 * q + 3]) * inv);
+          if (direct && p.ctx16_hi) {   // 32 consecutive columns e of row d = gk: half of one 64-element MN block
+            const int e0 = vb * 128 + c0;
+            const size_t o16 = (((size_t)b * (p.C >> 6) + (e0 >> 6)) * p.C + gk) * 64 + (e0 & 63);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(t[8 * q + k]) * inv;
+              uint4 hi, lo;
+              pack_out8(f, hi, lo, true);
+              *reinterpret_cast<uint4*>(p.ctx16_hi + o16 + 8 * q) = hi;
+              *reinterpret_cast<uint4*>(p.ctx16_lo + o16 + 8 * q) = lo;
+            }
+          }
         }
       }
       if (!direct && k_ok && vb == 0) {

@@ -23,6 +23,7 @@
 #include "igemm_hmma.cuh"
 #include "igemm_tc.cuh"
 #include "attn_tc.cuh"
+#include "attn_alg_tc.cuh"
 #include "misc.cuh"
 #include "final_tc.cuh"
 
@@ -71,6 +72,8 @@ struct AttnW {
   int C = 0;
   size_t wkv = 0, u = 0, c = 0;          // fp16 [C/64][2C][64], fp32 [2C], fp32 [2C]
   size_t wq = 0, woT = 0;                // fp32 [C][C] (scale folded), fp32 [C][C] transposed
+  size_t wq16h = 0, wq16l = 0;           // the same two matrices as fp16 value + remainder in the MN-blocked operand layout of
+  size_t wo16h = 0, wo16l = 0;           // attn_alg_tc_kernel: element (k, mn) at ((mn/64) * C + k) * 64 + mn % 64
   size_t g = 0, bln = 0, bout = 0;       // fp32 [C]
 };
 
@@ -84,7 +87,7 @@ struct Level {
 
 // ---------------------------------------------------------------- plan
 enum OpKind { OP_PACK, OP_CONV, OP_TIME, OP_ATTN_CTX, OP_COMBINE, OP_SGEMM, OP_FINISH, OP_FINAL, OP_ADVANCE, OP_LNROWS,
-              OP_LATENT, OP_UPSMALL };
+              OP_LATENT, OP_UPSMALL, OP_ALG };
 
 struct Op {
   int kind = 0;
@@ -97,7 +100,7 @@ struct Op {
   AttnCtxParams actx{};
   AttnTcParams atc{};      // tcgen05 form of the context kernel (use_tc; tensor maps in maps.a[0] / maps.b[0])
   int atc_smem = 0;
-  struct { const float *pc, *pm, *ps; int C, nchunks; float* out; } comb{};
+  struct { const float *pc, *pm, *ps; int C, nchunks; float* out; __half *o16h, *o16l; } comb{};
   struct { const float *At, *Bm; float* Cout; int M, N, K; long long sA, sB, sC; } sg{};
   GemmFinish gfin{};       // OP_SGEMM: fused finish epilogue (second attention product)
   struct { const float *Mf, *g, *bln, *bout; int C; __half* Mg; float *um, *cm; } fin{};
@@ -112,6 +115,8 @@ struct Op {
   int lane = 0;
   bool join_before = false;
   LnRowsParams lnr{};   // OP_LNROWS: second half of a sliced convolution
+  AlgTcParams alg{};    // OP_ALG: one C x C product of the attention algebra on tcgen05 (maps.a[0..1] = A hi/lo, maps.b[0..1] = B hi/lo)
+  struct { const __half *ah, *al, *bh, *bl; } algsrc{};
   UpSmallParams ups{};  // OP_UPSMALL: last Upsample of the eps context decoder (C_out <= 8, fp32 NCHW output)
   struct { __half *hi, *lo; int C, HW; } lat{};   // OP_LATENT: quantised latent fp32 NCHW -> NHWC hi + lo
   long long ctr_index = -1;   // K-split convolution with the fused finish: first of its 2 x tiles arrival counters
@@ -227,6 +232,8 @@ struct cdc_engine {
   bool dual_pass = true;   // W_hi / W_lo passes of the 3-pass convolutions share one activation load; CDC_DUAL_PASS=0: separate
   int slice_max_tiles = 100;   // layers with fewer 128-pixel output tiles (at the nominal batch of 8) run in sliced mode
   bool fuse_res = true;   // res_conv folded into block2 (second TMEM accumulator); CDC_FUSE_RES=0: separate launch
+  bool attn_area = true;   // attention pixel chunks grow with the image area (CDC_ATTN_AREA=0: fixed count, round-1 behaviour)
+  bool alg_tc = true;   // attention C x C products on tcgen05 (attn_alg_tc.cuh); CDC_ALG_TC=0: split-fp16 mma.sync kernel
   bool attn_tc = true;  // tcgen05 attention-context kernel (attn_tc.cuh); CDC_ATTN_TC=0: mma.sync kernel of attn.cuh
   bool nslice = true;  // fused column slices + cluster LayerNorm exchange; CDC_NSLICE=0: K-split fp32 partials + ln_rows_kernel
   bool fuse_lnrows = false;  // CDC_FUSE_LNROWS=1: K-split convolutions finish their rows in the same launch (per-tile arrival counters)
@@ -591,6 +598,25 @@ int pack_attn(cdc_engine* e, const std::string& p, int C, AttnW* out) {
     for (int ee = 0; ee < C; ++ee) woT[(size_t)ee * C + o] = wo->data[(size_t)o * C + ee];
   out->wq = put_f32(e, wq.data(), wq.size());
   out->woT = put_f32(e, woT.data(), woT.size());
+  {   // MN-blocked fp16 value / remainder copies: wq is [K = d][MN = c], woT is [K = e][MN = o]
+    std::vector<__half> h((size_t)C * C), l((size_t)C * C);
+    auto blocked = [&](const std::vector<float>& src, size_t* oh, size_t* ol) {
+      for (int k = 0; k < C; ++k)
+        for (int mn = 0; mn < C; ++mn) {
+          const float v = src[(size_t)k * C + mn];
+          const __half hv = __float2half_rn(v);
+          const size_t o = ((size_t)(mn >> 6) * C + k) * 64 + (mn & 63);
+          h[o] = hv;
+          l[o] = __float2half_rn(v - __half2float(hv));
+        }
+      *oh = e->blob.reserve(h.size() * 2);
+      memcpy(e->blob.at<__half>(*oh), h.data(), h.size() * 2);
+      *ol = e->blob.reserve(l.size() * 2);
+      memcpy(e->blob.at<__half>(*ol), l.data(), l.size() * 2);
+    };
+    blocked(wq, &out->wq16h, &out->wq16l);
+    blocked(woT, &out->wo16h, &out->wo16l);
+  }
   out->g = put_f32(e, g->data.data(), C);
   out->bln = put_f32(e, bl->data.data(), C);
   out->bout = put_f32(e, bo->data.data(), C);
@@ -903,14 +929,24 @@ struct Builder {
     // (K block, V block) pair keep 144 CTAs busy at the nominal batch of 8 and the partial buffers small.
     const bool ctx_tc = e->mainloop == 1 && e->attn_tc && (C == 64 || C == 128 || C == 192 || C == 256 || C == 320) && N % 64 == 0;
     const int pairs = C == 64 ? 1 : ((C + 127) / 128) * ((C + 127) / 128);
-    const int want_chunks = C == 64 ? 36 : std::max(1, 18 / pairs);   // C == 64 runs two CTAs per SM
-    const int tpc = ctx_tc ? (ntiles + want_chunks - 1) / want_chunks : std::max(8, (ntiles + 63) / 64);
+    // The chunk count grows with the image area (a function of H, W only — never of B): a single 512 x 768 image has as
+    // many pixels as six 256 x 256 ones and must fill the GPU on its own (the demo scripts decode one image at a time).
+    const int area = e->attn_area ? std::max(1, (pl->H * pl->W + 32768) / 65536) : 1;
+    const int want_chunks = std::min(kCombineMaxChunks, (C == 64 ? 36 : std::max(1, 18 / pairs)) * area);   // C == 64 runs two CTAs per SM
+    const int tpc = ctx_tc ? (ntiles + want_chunks - 1) / want_chunks
+                           : std::max(1, std::max(8, (ntiles + 63) / 64) / area);
     const int nchunks = (ntiles + tpc - 1) / tpc;
     const size_t pc_b = (size_t)B * nchunks * C * C * 4, pv_b = (size_t)B * nchunks * C * 4;
     const size_t pc = raw_alloc(pc_b), pm = raw_alloc(pv_b), ps = raw_alloc(pv_b);
     const size_t cc_b = (size_t)B * C * C * 4;
     const size_t ctxn = raw_alloc(cc_b);
     const bool direct = nchunks == 1;   // one pixel chunk: the context kernel writes ctx / S itself
+    // tcgen05 form of the two C x C products: ctx / S also leaves the producer as fp16 value + remainder (operand layout)
+    // (C >= 256 only: at C <= 192 the products are a few microseconds of launch latency either way and the mma.sync kernel's
+    // 64 x 64 tiles give more CTAs — measured 1-2 us faster per product)
+    const bool alg = e->mainloop == 1 && e->alg_tc && C >= 256;
+    const size_t c16_b = (size_t)B * C * C * 2;
+    const size_t c16h = alg ? raw_alloc(c16_b) : 0, c16l = alg ? raw_alloc(c16_b) : 0;
     {
       pl->ops.emplace_back();
       Op& op = pl->ops.back();
@@ -929,6 +965,8 @@ struct Builder {
       op.actx.part_m = ws<float>(pm);
       op.actx.part_s = ws<float>(ps);
       op.actx.ctxn = direct ? ws<float>(ctxn) : nullptr;
+      op.actx.ctx16_hi = (direct && alg) ? ws<__half>(c16h) : nullptr;
+      op.actx.ctx16_lo = (direct && alg) ? ws<__half>(c16l) : nullptr;
       op.grid = dim3(nchunks, cb * cb, B);
       if (ctx_tc) {
         op.use_tc = true;
@@ -944,6 +982,8 @@ struct Builder {
         q.u = op.actx.u; q.c = op.actx.c;
         q.part_ctx = op.actx.part_ctx; q.part_m = op.actx.part_m; q.part_s = op.actx.part_s;
         q.ctxn = op.actx.ctxn;
+        q.ctx16_hi = op.actx.ctx16_hi;
+        q.ctx16_lo = op.actx.ctx16_lo;
         op.grid = dim3(nchunks, pairs, B);
       }
       // to_qkv 1x1 (3C x C per pixel) + the two einsums (2 * C*C per pixel) + to_out (C x C per pixel)
@@ -954,10 +994,12 @@ struct Builder {
       Op& op = pl->ops.back();
       op.kind = OP_COMBINE;
       op.name = name + "combine";
-      op.comb = {ws<float>(pc), ws<float>(pm), ws<float>(ps), C, nchunks, ws<float>(ctxn)};
+      op.comb = {ws<float>(pc), ws<float>(pm), ws<float>(ps), C, nchunks, ws<float>(ctxn),
+                 alg ? ws<__half>(c16h) : nullptr, alg ? ws<__half>(c16l) : nullptr};
       op.grid = dim3(C, B, 1);
     }
     raw_free(pc, pc_b); raw_free(pm, pv_b); raw_free(ps, pv_b);
+    if (alg) return attention_tail_tc(name, x, stats, stats_off, stats_bytes, w, ctxn, cc_b, c16h, c16l, c16_b);
     const size_t T = raw_alloc(cc_b);
     {
       pl->ops.emplace_back();
@@ -999,6 +1041,16 @@ struct Builder {
       op.grid = dim3(C, B, 1);
     }
     raw_free(Mf, cc_b);
+    Act out = attention_out(name, x, stats, w, Mg, um, cm, parts);
+    raw_free(Mg, mg_b); raw_free(um, v_b); raw_free(cm, v_b);
+    raw_free(stats_off, stats_bytes);
+    return out;
+  }
+
+  // Output GEMM of the attention block: out = M_b-folded per-image weights applied to raw x (EPI_AFFINE) + residual.
+  Act attention_out(const std::string& name, const Act& x, float2* stats, const AttnW& w, size_t Mg, size_t um, size_t cm,
+                    int parts) {
+    const int C = w.C, N = x.H * x.W, cb = C / 64;
     Act out = new_act(C, x.H, x.W, true);
     {
       ConvW cw;
@@ -1045,6 +1097,47 @@ struct Builder {
       op.grid = dim3(B * ((N + op.bm - 1) / op.bm), C / op.bn, 1);
       op.flops = 0;
     }
+    return out;
+  }
+
+  // tcgen05 form of the per-image algebra: T = ctx^T (C^-1/2 W_q), M_b = W_out T with the finish epilogue — two launches of
+  // attn_alg_tc_kernel on MN-blocked fp16 value / remainder operands (attn_alg_tc.cuh).
+  Act attention_tail_tc(const std::string& name, const Act& x, float2* stats, size_t stats_off, size_t stats_bytes,
+                        const AttnW& w, size_t ctxn, size_t cc_b, size_t c16h, size_t c16l, size_t c16_b) {
+    const int C = w.C, cb = C / 64;
+    raw_free(ctxn, cc_b);
+    const size_t t16h = raw_alloc(c16_b), t16l = raw_alloc(c16_b);
+    auto alg_op = [&](const char* suffix, int mode) -> Op& {
+      pl->ops.emplace_back();
+      Op& op = pl->ops.back();
+      op.kind = OP_ALG;
+      op.name = name + suffix;
+      AlgTcParams& q = op.alg;
+      q.C = C; q.kchunks = cb; q.n_tiles = (C + 127) / 128; q.mode = mode;
+      q.stages = std::min(3, cb);
+      op.grid = dim3(q.n_tiles * q.n_tiles, 1, B);
+      return op;
+    };
+    {
+      Op& op = alg_op("T", 0);
+      op.alg.a_img = 1; op.alg.b_img = 0;
+      op.algsrc = {ws<__half>(c16h), ws<__half>(c16l), dptr<__half>(e, w.wq16h), dptr<__half>(e, w.wq16l)};
+      op.alg.out_hi = ws<__half>(t16h);
+      op.alg.out_lo = ws<__half>(t16l);
+    }
+    raw_free(c16h, c16_b); raw_free(c16l, c16_b);
+    const int parts = cb;
+    const size_t mg_b = (size_t)B * C * C * 2, v_b = (size_t)B * parts * C * 4;
+    const size_t Mg = raw_alloc(mg_b), um = raw_alloc(v_b), cm = raw_alloc(v_b);
+    {
+      Op& op = alg_op("M", 1);
+      op.alg.a_img = 0; op.alg.b_img = 1;
+      op.algsrc = {dptr<__half>(e, w.wo16h), dptr<__half>(e, w.wo16l), ws<__half>(t16h), ws<__half>(t16l)};
+      op.alg.g = dptr<float>(e, w.g); op.alg.bln = dptr<float>(e, w.bln); op.alg.bout = dptr<float>(e, w.bout);
+      op.alg.Mg16 = ws<__half>(Mg); op.alg.um_part = ws<float>(um); op.alg.cm_part = ws<float>(cm);
+    }
+    raw_free(t16h, c16_b); raw_free(t16l, c16_b);
+    Act out = attention_out(name, x, stats, w, Mg, um, cm, parts);
     raw_free(Mg, mg_b); raw_free(um, v_b); raw_free(cm, v_b);
     raw_free(stats_off, stats_bytes);
     return out;
@@ -1620,6 +1713,26 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(final conv input) failed: %d", (int)r);
       }
+      if (op.kind == OP_ALG && pl->ws) {
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        const cuuint64_t C = (cuuint64_t)op.alg.C;
+        const __half* src[4] = {op.algsrc.ah, op.algsrc.al, op.algsrc.bh, op.algsrc.bl};
+        for (int i = 0; i < 4; ++i) {
+          const bool per_img = i < 2 ? op.alg.a_img != 0 : op.alg.b_img != 0;
+          // MN-blocked operand [image][MN / 64][K][64]: view {64, K, MN blocks, image}
+          cuuint64_t gdim[4] = {64, C, C / 64, (cuuint64_t)(per_img ? pl->B : 1)};
+          cuuint64_t gstr[3] = {128, C * 128, C * C * 2};
+          cuuint32_t box[4] = {64, 64, 2, 1};
+          cuuint32_t estr[4] = {1, 1, 1, 1};
+          CUtensorMap* m = i < 2 ? &op.maps.a[i] : &op.maps.b[i - 2];
+          CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)src[i], gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS)
+            return fail(e, CDC_ERR_CUDA, "cuTensorMapEncodeTiled(attention algebra operand %d, op %s) failed: %d", i, op.name.c_str(), (int)r);
+        }
+      }
       if (op.kind != OP_CONV) { ops2.push_back(op); continue; }
       int rc = setup_tc(e, pl, op);
       if (rc) return rc;
@@ -1718,7 +1831,7 @@ bool pdl_for(const cdc_engine* e, const Op& op) {
   if (e->pdl_mode == 1) return true;
   const bool cluster_conv = op.kind == OP_CONV && op.use_tc && op.tcp.cluster_n > 1;
   if (e->pdl_mode == 2) return cluster_conv;
-  const bool small = op.kind == OP_SGEMM || op.kind == OP_COMBINE || op.kind == OP_LNROWS || op.kind == OP_FINISH ||
+  const bool small = op.kind == OP_SGEMM || op.kind == OP_ALG || op.kind == OP_COMBINE || op.kind == OP_LNROWS || op.kind == OP_FINISH ||
                      (op.kind == OP_CONV && op.use_tc && op.tc_grid <= e->num_sms);
   return cluster_conv || small;
 }
@@ -1769,7 +1882,10 @@ int run_op(cdc_engine* e, Plan* pl, const Op& op, size_t i, const RunArgs& a, cu
         break;
       case OP_COMBINE:
         launch_k(attn_combine_kernel, op.grid, dim3(128), 0, st, op.comb.pc, op.comb.pm, op.comb.ps, op.comb.C,
-                 op.comb.nchunks, op.comb.out);
+                 op.comb.nchunks, op.comb.out, op.comb.o16h, op.comb.o16l);
+        break;
+      case OP_ALG:
+        launch_k(attn_alg_tc_kernel, op.grid, dim3(kAlgThreads), (size_t)alg_tc_smem_bytes(op.alg.stages), st, op.maps, op.alg);
         break;
       case OP_SGEMM:
         launch_k(gemm3xf16_tn_kernel, op.grid, dim3(128), (size_t)Gemm3xSmem::kBytes, st, op.sg.At, op.sg.Bm,
@@ -1980,6 +2096,8 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_NSLICE")) e->nslice = atoi(v) != 0;
   if (const char* v = getenv("CDC_FUSE_LNROWS")) e->fuse_lnrows = atoi(v) != 0;
   if (const char* v = getenv("CDC_ATTN_TC")) e->attn_tc = atoi(v) != 0;
+  if (const char* v = getenv("CDC_ALG_TC")) e->alg_tc = atoi(v) != 0;
+  if (const char* v = getenv("CDC_ATTN_AREA")) e->attn_area = atoi(v) != 0;
   if (const char* v = getenv("CDC_FUSE_RES")) e->fuse_res = atoi(v) != 0;
   if (const char* v = getenv("CDC_DUAL_PASS")) e->dual_pass = atoi(v) != 0;
   if (const char* v = getenv("CDC_SLICE_MAXTILES")) e->slice_max_tiles = std::max(1, atoi(v));
@@ -1991,6 +2109,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_SLICE_KMAX")) e->slice_kmax = std::max(1, atoi(v));
   cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCtxSmem::kBytes);
   cudaFuncSetAttribute(attn_ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(attn_alg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(gemm3xf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm3xSmem::kBytes);
   cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes);
   cudaFuncSetAttribute(final_conv_kx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes2);

@@ -1,0 +1,62 @@
+"""Multi-GPU path: the batch is split across ranks, every rank decodes its shard through compress() and one
+NCCL all-gather returns the full batch.  Gate: the G-rank result is BIT-IDENTICAL to the 1-rank result (no kernel's
+summation order depends on the batch it runs in).  Needs >= 2 devices: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import functools, os, sys, torch, torch.distributed as dist
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+from conftest import build_dropin
+from oracle import cdc_oracle as O
+from cdc_compression_b200 import parallel
+torch.set_grad_enabled(False)
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+variant = sys.argv[2]
+d = build_dropin(variant)
+d.load_state_dict(O.seeded_fill(d.state_dict(), seed=0, denoiser_gain=0.5))
+if variant == "eps":
+    d.clip_noise = "full"
+d.to(dev)
+g = torch.Generator().manual_seed(7)                 # every rank draws the SAME global batch before the split
+images = (torch.rand(5, 3, 64, 96, generator=g) * 2 - 1).to(dev)
+init = (torch.randn(5, 3, 64, 96, generator=g) * 0.8).to(dev)
+kw = dict(sample_steps=5, bpp_return_mean=False)
+if variant == "eps":
+    kw["sample_mode"] = "ddim"
+out, bpp = parallel.sharded_decode(functools.partial(d.compress, **kw), images, init=init)
+ref, rbpp = d.compress(images, init=init, **kw)       # the whole batch on this rank alone
+assert out.shape == ref.shape and torch.equal(out, ref), f"rank {rank}: sharded decode differs, max {(out - ref).abs().max().item()}"
+assert torch.equal(bpp, rbpp.reshape(-1))
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+@pytest.mark.parametrize("variant", ["eps", "x"])
+def test_sharded_decode_is_bit_identical_to_single_rank(tmp_path, variant):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29540 + (0 if variant == "eps" else 1)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, variant], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0 and "ok" in out, out[-3000:]
