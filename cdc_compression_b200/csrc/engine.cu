@@ -931,6 +931,9 @@ struct Builder {
     const int pairs = C == 64 ? 1 : ((C + 127) / 128) * ((C + 127) / 128);
     // The chunk count grows with the image area (a function of H, W only — never of B): a single 512 x 768 image has as
     // many pixels as six 256 x 256 ones and must fill the GPU on its own (the demo scripts decode one image at a time).
+    // Measured (round 2): proportional growth takes the single 512 x 768 image from 3.00 to 2.45 ms/step and costs a batch
+    // of eight 512 x 512 images 3 % (their context kernels go from one wave of CTAs to several); sqrt growth costs the
+    // batch the same 3 % and gives the single image only 2.55 ms.  Proportional it is.
     const int area = e->attn_area ? std::max(1, (pl->H * pl->W + 32768) / 65536) : 1;
     const int want_chunks = std::min(kCombineMaxChunks, (C == 64 ? 36 : std::max(1, 18 / pairs)) * area);   // C == 64 runs two CTAs per SM
     const int tpc = ctx_tc ? (ntiles + want_chunks - 1) / want_chunks

@@ -16,6 +16,7 @@ ap.add_argument("--H", type=int, default=256)
 ap.add_argument("--W", type=int, default=256)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--mainloop", type=int, default=1)
+ap.add_argument("--names-out", default=None, help="write the plan's op names (launch order of one forward) as JSON")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 eng = DenoiserEngine(a.variant, 64, (1, 2, 3, 4, 5, 6), (1, 2, 3, 4), 3, 3 if a.variant == "eps" else 64, dev)
@@ -27,4 +28,7 @@ t = torch.full((a.B,), 0.5, device=dev)
 for _ in range(a.iters):
     y = eng.forward(x, t, ctx)
 torch.cuda.synchronize()
+if a.names_out:
+    import json
+    json.dump(eng.debug_ops(a.B, a.H, a.W), open(a.names_out, "w"))
 print("ok", float(y.abs().mean()), "tc ops", eng.tc_ops(a.B, a.H, a.W))

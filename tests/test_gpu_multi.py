@@ -30,8 +30,8 @@ if variant == "eps":
     d.clip_noise = "full"
 d.to(dev)
 g = torch.Generator().manual_seed(7)                 # every rank draws the SAME global batch before the split
-images = (torch.rand(5, 3, 64, 96, generator=g) * 2 - 1).to(dev)
-init = (torch.randn(5, 3, 64, 96, generator=g) * 0.8).to(dev)
+images = (torch.rand(5, 3, 64, 128, generator=g) * 2 - 1).to(dev)
+init = (torch.randn(5, 3, 64, 128, generator=g) * 0.8).to(dev)
 kw = dict(sample_steps=5, bpp_return_mean=False)
 if variant == "eps":
     kw["sample_mode"] = "ddim"
