@@ -240,6 +240,7 @@ struct cdc_engine {
                              // instead of ln_rows_kernel.  Measured (B=8 256x256): 16 launches fewer but 2.653 vs 2.633 ms/step —
                              // fence + arrival atomics + the wait for the tile's slowest unit cost what the launch did; off.
   int slice_slots = 148, slice_kmax = 64;   // tuning knobs (CDC_SLICE_SLOTS / CDC_SLICE_KMAX)
+  bool profiling = false;                   // cdc_engine_profile_ops in progress: launches are timed alone, without PDL overlap
   int pdl_mode = 1;                         // CDC_PDL: programmatic dependent launch policy (see pdl_for)
   // derived structure
   std::vector<int> dims, cdims;
@@ -278,6 +279,7 @@ struct cdc_engine {
   cudaStream_t side_stream = nullptr;   // second lane of the step (see Op::lane)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool two_lanes = true;                // CDC_TWO_LANES=0: everything on one stream
+  bool time_lane = true;                // timestep MLP on the side lane (overlaps pack_input); CDC_TIME_LANE=0: main lane
   // context state
   bool ctx_set = false;
   int ctx_B = 0, ctx_H = 0, ctx_W = 0;
@@ -734,6 +736,7 @@ struct Builder {
   Arena arena;
   size_t arena_base = 0;
   int B, H, W;
+  bool pending_time_join = false;
 
   template <typename T>
   T* ws(size_t off) { return reinterpret_cast<T*>(pl->ws + off); }  // valid arithmetic even for ws == nullptr (dry run)
@@ -851,6 +854,8 @@ struct Builder {
     Act h1 = new_act(w.cout, h, wd);
     {
       Op& op = conv(name + "block1", segs1, w.b1.conv, EPI_LN_SHIFT, h1, 1, 0);
+      op.join_before = pending_time_join;   // the first block1 of the plan waits for the timestep MLP on the side lane
+      pending_time_join = false;
       op.conv.ln_g = dptr<float>(e, w.b1.g);
       op.conv.ln_b = dptr<float>(e, w.b1.b);
       op.conv.shift = w.shift_off >= 0 ? ws<float>(pl->shifts_off) + w.shift_off : nullptr;
@@ -1553,7 +1558,10 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     Op& op = pl->ops.back();
     op.kind = OP_TIME;
     op.name = "time_mlp";
+    // side lane: the timestep MLP only feeds the shift vectors of the first block1 epilogue; it overlaps pack_input
+    op.lane = (e->two_lanes && e->time_lane) ? 1 : 0;
     pl->time_op = (int)pl->ops.size() - 1;
+    bd.pending_time_join = op.lane == 1;
   }
   Act x0 = bd.new_act(64, H, W);
   {
@@ -1830,7 +1838,7 @@ Plan* get_plan(cdc_engine* e, int B, int H, int W, void* ws, int* rc) {
 // thread-block-cluster convolutions, 3 = mode 2 + every small-grid kernel.  Round 2, B=8 256x256: 2.631 (0) / 2.608 (2) /
 // 2.590 (3) / 2.570 (1) ms per step.  (Round 1 measured mode 1 as a loss on a 4.7 ms step; launches were longer then.)
 bool pdl_for(const cdc_engine* e, const Op& op) {
-  if (e->pdl_mode <= 0) return false;
+  if (e->pdl_mode <= 0 || e->profiling) return false;   // per-op profiling times every launch in plain stream order
   if (e->pdl_mode == 1) return true;
   const bool cluster_conv = op.kind == OP_CONV && op.use_tc && op.tcp.cluster_n > 1;
   if (e->pdl_mode == 2) return cluster_conv;
@@ -2106,6 +2114,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_SLICE_MAXTILES")) e->slice_max_tiles = std::max(1, atoi(v));
   if (const char* v = getenv("CDC_FOLD_FINISH")) e->fold_finish = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
+  if (const char* v = getenv("CDC_TIME_LANE")) e->time_lane = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
   if (const char* v = getenv("CDC_PDL")) e->pdl_mode = atoi(v);
   if (const char* v = getenv("CDC_SLICE_SLOTS")) e->slice_slots = std::max(1, atoi(v));
@@ -2584,6 +2593,11 @@ int cdc_engine_profile_ops(cdc_engine* e, int iters, float* ms_out, double* flop
   args.advance = false;
   long long* clkbuf = nullptr;
   if (getenv("CDC_DBG_CLK")) cudaMallocManaged(&clkbuf, 16 * sizeof(long long));
+  struct ProfilingScope {
+    cdc_engine* e;
+    explicit ProfilingScope(cdc_engine* e_) : e(e_) { e->profiling = true; }
+    ~ProfilingScope() { e->profiling = false; }
+  } profiling_scope(e);
   for (int i = 0; i < n; ++i) {
     if (clkbuf) {
       cudaDeviceSynchronize();

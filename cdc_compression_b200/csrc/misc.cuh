@@ -189,23 +189,40 @@ __global__ void time_mlp_kernel(const float* __restrict__ time, const cdc_step_c
     hid[j] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
   }
   __syncthreads();
-  for (int j = threadIdx.x >> 2; j < dim; j += blockDim.x >> 2) {   // 4 lanes per output
-    const float* w = W2 + (size_t)j * 4 * dim;
+  // layer 2: one warp per output, coalesced float4 rows (4*dim is a multiple of 128), shuffle reduction in a fixed order
+  for (int j = threadIdx.x >> 5; j < dim; j += blockDim.x >> 5) {
+    const float4* w = reinterpret_cast<const float4*>(W2 + (size_t)j * 4 * dim);
+    const float4* h4 = reinterpret_cast<const float4*>(hid);
     float a = 0.f;
-    for (int k = threadIdx.x & 3; k < 4 * dim; k += 4) a = fmaf(w[k], hid[k], a);
-    a += __shfl_xor_sync(0xffffffffu, a, 1);
-    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    for (int k = threadIdx.x & 31; k < dim; k += 32) {
+      const float4 wv = w[k], hv = h4[k];
+      a = fmaf(wv.x, hv.x, a);
+      a = fmaf(wv.y, hv.y, a);
+      a = fmaf(wv.z, hv.z, a);
+      a = fmaf(wv.w, hv.w, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     a += b2[j];
-    if ((threadIdx.x & 3) == 0) act[j] = a > 0.f ? a : 0.2f * a;
+    if ((threadIdx.x & 31) == 0) act[j] = a > 0.f ? a : 0.2f * a;
   }
   __syncthreads();
-  // blockIdx.y selects a 256-row slice of the concatenated per-block Linear layers (temb is recomputed per CTA)
+  // blockIdx.y selects a 256-row slice of the concatenated per-block Linear layers (temb is recomputed per CTA); a row is
+  // dim floats: sixteen 16-byte loads issued together instead of 64 dependent scalar ones
   const int r = blockIdx.y * blockDim.x + threadIdx.x;
   if (r < R) {
-    float a = bcat[r];
-    const float* w = Wcat + (size_t)r * dim;
-    for (int k = 0; k < dim; ++k) a = fmaf(w[k], act[k], a);
-    shifts[(size_t)b * R + r] = a;
+    const float4* w = reinterpret_cast<const float4*>(Wcat + (size_t)r * dim);
+    const float4* a4 = reinterpret_cast<const float4*>(act);
+    float a0 = bcat[r], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < dim / 4; ++k) {
+      const float4 wv = w[k], av = a4[k];
+      a0 = fmaf(wv.x, av.x, a0);
+      a1 = fmaf(wv.y, av.y, a1);
+      a2 = fmaf(wv.z, av.z, a2);
+      a3 = fmaf(wv.w, av.w, a3);
+    }
+    shifts[(size_t)b * R + r] = (a0 + a1) + (a2 + a3);
   }
 }
 
