@@ -1367,6 +1367,7 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op, bool allow_dual = true) {
     else pl->raw_bytes = std::max(pl->raw_bytes, need);
     t.raw = nullptr;
   }
+  t.dbg_skip_epi = (getenv("CDC_DBG_EPI") && atoi(getenv("CDC_DBG_EPI")) && t.cluster_n <= 1 && t.epi != EPI_RAW) ? 1 : 0;
   t.fd_upt = make_fastdiv((uint32_t)(t.n_slices * t.k_splits));
   t.fd_ks = make_fastdiv((uint32_t)t.k_splits);
   t.fd_tpp = make_fastdiv((uint32_t)(t.tiles_x * t.tiles_y * t.tiles_b));
