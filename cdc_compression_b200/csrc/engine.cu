@@ -228,6 +228,7 @@ struct cdc_engine {
   size_t w_ident = 0;     // [64][64] fp16 identity "weights": identity residual of a 64-channel block through the MMA
   bool final_preln = true;  // last Upsample writes the LayerNorm-ed fp16 input of the final conv; CDC_FINAL_PRELN=0: final conv normalises
   bool final_tc = true; // tcgen05 form of the final conv (final_tc.cuh); CDC_FINAL_TC=0: mma.sync form
+  bool final_persist = true;  // persistent, double-buffered tcgen05 final conv; CDC_FINAL_PERSIST=0: one tile per CTA
   bool fold_finish = true;   // attn_finish_kernel fused into the second C x C product; CDC_FOLD_FINISH=0: separate kernel
   bool dual_pass = true;   // W_hi / W_lo passes of the 3-pass convolutions share one activation load; CDC_DUAL_PASS=0: separate
   int slice_max_tiles = 100;   // layers with fewer 128-pixel output tiles (at the nominal batch of 8) run in sliced mode
@@ -1930,7 +1931,11 @@ int run_op(cdc_engine* e, Plan* pl, const Op& op, size_t i, const RunArgs& a, cu
         fp.clip_mode = a.clip;
         if (e->has_f_w2 && e->final_tc && e->mainloop == 1) {
           fp.Wf = dptr<__half>(e, e->f_w3);
-          if (op.conv.seg[2].src)
+          if (op.conv.seg[2].src && e->final_persist) {
+            const int total = (W / 16) * (H / 16) * B;
+            launch_k(final_conv_tc_persist_kernel, dim3(std::min(total, e->num_sms)), dim3(kFinalPersistThreads),
+                     (size_t)kFinalSmemBytesP, st, fp, op.maps.a[0], W / 16, H / 16, total);
+          } else if (op.conv.seg[2].src)
             launch_k(final_conv_tc_kernel<true>, dim3(W / 16, H / 16, B), dim3(256), (size_t)kFinalSmemBytes3, st, fp,
                      op.maps.a[0]);
           else
@@ -2128,6 +2133,8 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   cudaFuncSetAttribute(final_conv_kx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes2);
   cudaFuncSetAttribute(final_conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes3);
   cudaFuncSetAttribute(final_conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytes3);
+  cudaFuncSetAttribute(final_conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalSmemBytesP);
+  if (const char* v = getenv("CDC_FINAL_PERSIST")) e->final_persist = atoi(v) != 0;
   if (const char* v = getenv("CDC_FINAL_PRELN")) e->final_preln = atoi(v) != 0;
   if (const char* v = getenv("CDC_FINAL_TC")) e->final_tc = atoi(v) != 0;
   if (const char* v = getenv("CDC_FINAL_KX")) e->final_kx = atoi(v) != 0;

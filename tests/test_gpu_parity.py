@@ -340,6 +340,7 @@ KERNEL_FORMS = [("CDC_ATTN_TC", "mma.sync attention-context kernel instead of th
                 ("CDC_DUAL_PASS", "separate W_hi / W_lo passes instead of one activation load feeding two weight tiles"),
                 ("CDC_FUSE_RES", "separate res_conv launches instead of the second TMEM accumulator in block2"),
                 ("CDC_FINAL_PRELN", "final convolution normalises its own halo instead of reading the last Upsample's LayerNorm-ed copy"),
+                ("CDC_FINAL_PERSIST", "persistent double-buffered final convolution vs one 16 x 16 tile per CTA"),
                 ("CDC_ALG_TC", "attention C x C products on tcgen05 (MN-major operands) vs the split-fp16 mma.sync kernel"),
                 ("CDC_PDL", "programmatic dependent launch on every kernel (default) vs plain stream order"),
                 ("CDC_FUSE_LNROWS", "K-split convolutions finish their rows in the launch (arrival counters) vs the separate ln_rows_kernel")]
