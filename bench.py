@@ -382,6 +382,24 @@ def run_ours(args, wl):
     h2d = (images_p[lo:hi].numel() + init_p[lo:hi].numel()) * 4 / Ke
     d2h = out_host.numel() * 4 / Ke
 
+    # ---- per-op timing (each op alone, CUDA events) -> dominant kernel + per-block table.  Rank 0 only, and BEFORE the
+    # secondary measurement: thirty 8 x 512 x 512 steps leave the part power-limited for a while, and launches timed right
+    # after them read 5-10 % slow (round 2: roofline.frac 0.207 after, 0.224 before, same build, same step time).
+    prof = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        model.set_sample_schedule(S, device)
+        xs = init_d.clone().contiguous()
+        eng = model._bind(xs, ctx, 0.0)
+        eng.set_context(ctx, B, H, W)
+        eng.ddim_step(xs, S - 1, None, wl.pred, wl.clip)
+        prof = eng.profile_ops(iters=5)
+        if args.ops_out:
+            with open(args.ops_out, "w") as f:
+                json.dump([{"op": n, "ms": m, "gflop": fl / 1e9, "tflops": (fl / (m * 1e-3) / 1e12) if m > 0 else 0.0}
+                           for n, m, fl in prof], f, indent=0)
+        del xs
+
     # ---- secondary: BASELINE config 4's per-GPU shard (8 x 512x512), a few steps, device-resident (default run only) ----
     secondary = None
     if wl.name == "2" and not args.no_secondary:
@@ -423,18 +441,6 @@ def run_ours(args, wl):
             dist.destroy_process_group()
         return
 
-    # ---- per-op timing (each op alone, CUDA events) -> dominant kernel + per-block table ----
-    torch.cuda.synchronize()
-    model.set_sample_schedule(S, device)
-    xs = init_d.clone().contiguous()
-    eng = model._bind(xs, ctx, 0.0)
-    eng.set_context(ctx, B, H, W)
-    eng.ddim_step(xs, S - 1, None, wl.pred, wl.clip)
-    prof = eng.profile_ops(iters=5)
-    if args.ops_out:
-        with open(args.ops_out, "w") as f:
-            json.dump([{"op": n, "ms": m, "gflop": fl / 1e9, "tflops": (fl / (m * 1e-3) / 1e12) if m > 0 else 0.0}
-                       for n, m, fl in prof], f, indent=0)
     tot_ms = sum(p[1] for p in prof)
     fam = {}
     for name, pms, fl in prof:

@@ -280,6 +280,7 @@ struct cdc_engine {
   cudaStream_t side_stream = nullptr;   // second lane of the step (see Op::lane)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool two_lanes = true;                // CDC_TWO_LANES=0: everything on one stream
+  bool lnrows_hoist = true;             // small-grid ln_rows_kernel loads its vectors before the partials (CDC_LNROWS_HOIST=0: compact form)
   bool time_lane = true;                // timestep MLP on the side lane (overlaps pack_input); CDC_TIME_LANE=0: main lane
   // context state
   bool ctx_set = false;
@@ -1905,7 +1906,8 @@ int run_op(cdc_engine* e, Plan* pl, const Op& op, size_t i, const RunArgs& a, cu
                  op.sg.Cout, op.sg.M, op.sg.N, op.sg.K, op.sg.sA, op.sg.sB, op.sg.sC, op.gfin);
         break;
       case OP_LNROWS:
-        launch_k(ln_rows_kernel, op.grid, dim3(256), 0, st, op.lnr);
+        if (e->lnrows_hoist && (int)op.grid.x <= e->num_sms) launch_k(ln_rows_kernel<true>, op.grid, dim3(256), 0, st, op.lnr);
+        else launch_k(ln_rows_kernel<false>, op.grid, dim3(256), 0, st, op.lnr);
         break;
       case OP_FINISH:
         launch_k(attn_finish_kernel, op.grid, dim3(128), 0, st, op.fin.Mf, op.fin.g, op.fin.bln, op.fin.bout, op.fin.C,
@@ -2121,6 +2123,7 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   if (const char* v = getenv("CDC_FOLD_FINISH")) e->fold_finish = atoi(v) != 0;
   if (const char* v = getenv("CDC_TWO_LANES")) e->two_lanes = atoi(v) != 0;
   if (const char* v = getenv("CDC_TIME_LANE")) e->time_lane = atoi(v) != 0;
+  if (const char* v = getenv("CDC_LNROWS_HOIST")) e->lnrows_hoist = atoi(v) != 0;
   if (const char* v = getenv("CDC_VREUSE")) e->vreuse = atoi(v);
   if (const char* v = getenv("CDC_PDL")) e->pdl_mode = atoi(v);
   if (const char* v = getenv("CDC_SLICE_SLOTS")) e->slice_slots = std::max(1, atoi(v));

@@ -7,7 +7,7 @@
     repo), whole tensor and the 1-pixel border ring separately, at 64x96 and at 256x256;
   * long trajectories from the reference: eps S=50 (small-gain weights), x S=65 (the demo default), and the x
     variant's pred_mode "noise" / "v" branches (xparam/modules/denoising_diffusion.py:157-165).
-Margins are printed (run with -s) and collected in profiles/parity_r02.json by tests/gpu_parity_report.py.
+Margins are printed (`pytest -m gpu -s | grep parity`); the round's values are committed as profiles/parity_r02.txt.
 """
 import copy
 import os
