@@ -49,6 +49,8 @@ _SIGNATURES = {
                                 C.c_int64, _P]),
     "cdc_sample_loop": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                   C.c_int64, _P]),
+    "cdc_sample_loop_noise": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P,
+                                        C.c_int64, _P]),
     "cdc_engine_launches_per_forward": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "cdc_engine_launches_per_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "cdc_engine_flops_per_forward": (C.c_double, [_P, C.c_int, C.c_int, C.c_int]),

@@ -172,9 +172,27 @@ class DiffusionBase(nn.Module):
             eng.sample_loop(x, S - 1, 0, pred_mode, clip_mode)
             self._advance_rng_like_reference(x, S)
         else:
-            for i in reversed(range(S)):
-                eng.ddim_step(x, i, torch.randn_like(x), pred_mode, clip_mode)
+            # eta != 0: the reference draws randn_like(x) every step.  The noise of a chunk of steps is drawn up front —
+            # one generator call per step, in loop order, so the random stream is exactly the reference's — and the
+            # chunk then runs as CUDA-graph replays with no PyTorch op in between.
+            cap = int(os.environ.get("CDC_NOISE_STEPS", "0")) or max(1, min(64, (128 << 20) // (x.numel() * 4)))
+            z = self._noise_buffer(x, min(cap, S))
+            i = S - 1
+            while i >= 0:
+                n = min(z.shape[0], i + 1)
+                for j in range(n):
+                    torch.randn(x.shape, out=z[j])
+                eng.sample_loop_noise(x, i, i - n + 1, z, pred_mode, clip_mode)
+                i -= n
         return x
+
+    def _noise_buffer(self, x, steps):
+        """Cached [steps, *x.shape] buffer: a stable address keeps the captured graph valid across decodes."""
+        buf = getattr(self, "_zbuf", None)
+        if buf is None or buf.device != x.device or tuple(buf.shape[1:]) != tuple(x.shape) or buf.shape[0] < steps:
+            buf = torch.empty((steps,) + tuple(x.shape), dtype=torch.float32, device=x.device)
+            self._zbuf = buf
+        return buf
 
     def _single_step(self, x, t, context, eta, pred_mode, clip_mode):
         """``ddim(x, t, ...)`` for callers that drive the loop themselves.  The engine advances the whole batch at ONE

@@ -195,6 +195,7 @@ struct Plan {
   // captured step graph
   cudaGraphExec_t graph = nullptr;
   int graph_pred = -1, graph_clip = -1;
+  const float* graph_z = nullptr;   // noise buffer the graph was captured with (null: eta == 0 loop)
 };
 
 }  // namespace
@@ -205,6 +206,7 @@ struct RunArgs {
   float* out = nullptr;         // mode 0
   float* x_inout = nullptr;     // mode 1
   const float* z = nullptr;
+  bool z_chunk = false;            // z holds the noise of consecutive steps (indexed from e->d_zfirst inside the kernels)
   const float* latent = nullptr;   // context decode: quantised latent, fp32 NCHW
   int mode = 0, pred = 0, clip = 0;
   bool advance = false;
@@ -273,6 +275,7 @@ struct cdc_engine {
   int h_table_cap = 0;
   cudaEvent_t ev_table = nullptr;
   int* d_step = nullptr;
+  int* d_zfirst = nullptr;   // schedule index whose noise sits first in the caller's z buffer (eta != 0 loops)
   // stream the sampling loop runs on (the caller's stream may be the legacy default stream, which
   // cannot be captured); joined to the caller's stream with events on both sides
   cudaStream_t loop_stream = nullptr;
@@ -1926,6 +1929,8 @@ int run_op(cdc_engine* e, Plan* pl, const Op& op, size_t i, const RunArgs& a, cu
         fp.out = a.out;
         fp.x = a.x_inout;
         fp.z = a.z;
+        fp.z_first = a.z_chunk ? e->d_zfirst : nullptr;
+        fp.z_stride = (long long)B * cfg.channels * H * W;
         fp.table = e->d_table;
         fp.step_ptr = e->d_step;
         fp.variant = cfg.variant;
@@ -2100,7 +2105,8 @@ int cdc_engine_create(const cdc_config* cfg, int device, cdc_engine** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) return fail(nullptr, CDC_ERR_UNSUPPORTED, "device sm_%d%d: this build targets sm_100a only", prop.major, prop.minor);
-  if (cudaMalloc(&e->d_step, sizeof(int)) != cudaSuccess) return fail(nullptr, CDC_ERR_CUDA, "cudaMalloc failed");
+  if (cudaMalloc(&e->d_step, sizeof(int)) != cudaSuccess || cudaMalloc(&e->d_zfirst, sizeof(int)) != cudaSuccess)
+    return fail(nullptr, CDC_ERR_CUDA, "cudaMalloc failed");
   if (cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess)
@@ -2153,6 +2159,7 @@ void cdc_engine_destroy(cdc_engine* e) {
   if (e->dblob) cudaFree(e->dblob);
   if (e->d_table) cudaFree(e->d_table);
   if (e->d_step) cudaFree(e->d_step);
+  if (e->d_zfirst) cudaFree(e->d_zfirst);
   if (e->loop_stream) cudaStreamDestroy(e->loop_stream);
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -2488,8 +2495,8 @@ int cdc_ddim_step(cdc_engine* e, float* x_inout, int i, const float* z, int pred
   return run_plan(e, pl, a, st);
 }
 
-int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int pred_mode, int clip_mode, int B, int H,
-                    int W, void* workspace, int64_t workspace_bytes, void* stream) {
+static int sample_loop_impl(cdc_engine* e, float* x_inout, int i_first, int i_last, const float* z, int pred_mode,
+                            int clip_mode, int B, int H, int W, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!e) return CDC_ERR_INVALID;
   if (!x_inout) return fail(e, CDC_ERR_INVALID, "null x");
   DeviceGuard dg(e->device);
@@ -2507,10 +2514,12 @@ int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int 
   auto body = [&]() -> int {
     int i_start = i_first;
     CUDA_TRY(e, cudaMemcpyAsync(xs, x_inout, xbytes, cudaMemcpyDeviceToDevice, st));
-    if (!pl->graph || pl->graph_pred != pred_mode || pl->graph_clip != clip_mode) {
+    if (z) set_int_kernel<<<1, 32, 0, st>>>(e->d_zfirst, i_first);
+    if (!pl->graph || pl->graph_pred != pred_mode || pl->graph_clip != clip_mode || pl->graph_z != z) {
       if (pl->graph) { cudaGraphExecDestroy(pl->graph); pl->graph = nullptr; }
       RunArgs a;
-      a.x = xs; a.x_inout = xs; a.z = nullptr; a.mode = 1; a.pred = pred_mode; a.clip = clip_mode; a.advance = true;
+      a.x = xs; a.x_inout = xs; a.z = z; a.z_chunk = z != nullptr; a.mode = 1; a.pred = pred_mode; a.clip = clip_mode;
+      a.advance = true;
       // The first step runs eagerly: it is real work AND it forces every kernel's module load /
       // attribute setup to happen before stream capture starts.
       set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
@@ -2526,7 +2535,7 @@ int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int 
       err = cudaGraphInstantiate(&pl->graph, g, 0);
       cudaGraphDestroy(g);
       if (err != cudaSuccess) { pl->graph = nullptr; return fail(e, CDC_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(err)); }
-      pl->graph_pred = pred_mode; pl->graph_clip = clip_mode;
+      pl->graph_pred = pred_mode; pl->graph_clip = clip_mode; pl->graph_z = z;
     } else {
       set_int_kernel<<<1, 32, 0, st>>>(e->d_step, i_first);
     }
@@ -2542,6 +2551,17 @@ int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int 
   if (j2 != cudaSuccess) return fail(e, CDC_ERR_CUDA, "joining the loop stream failed: %s", cudaGetErrorString(j2));
   e->last_plan = pl;
   return CDC_OK;
+}
+
+int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int pred_mode, int clip_mode, int B, int H,
+                    int W, void* workspace, int64_t workspace_bytes, void* stream) {
+  return sample_loop_impl(e, x_inout, i_first, i_last, nullptr, pred_mode, clip_mode, B, H, W, workspace, workspace_bytes, stream);
+}
+
+int cdc_sample_loop_noise(cdc_engine* e, float* x_inout, int i_first, int i_last, const float* z, int pred_mode,
+                          int clip_mode, int B, int H, int W, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (e && !z) return fail(e, CDC_ERR_INVALID, "null noise buffer");
+  return sample_loop_impl(e, x_inout, i_first, i_last, z, pred_mode, clip_mode, B, H, W, workspace, workspace_bytes, stream);
 }
 
 int cdc_engine_launches_per_forward(cdc_engine* e, int B, int H, int W) {

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) final_conv_tc_kernel(const FinalParams p,
       noise = (cf.sqrt_recip_acp * xt - x0v) / cf.sqrt_recipm1_acp;
     }
     float xn = cf.sqrt_acp_prev * x0v + cf.dir_coef * noise;
-    if (p.z) xn += cf.noise_coef * p.z[idx];
+    if (p.z) xn += cf.noise_coef * final_noise(p)[idx];
     p.x[idx] = xn;
   }
 }
@@ -363,7 +363,7 @@ final_conv_tc_persist_kernel(const FinalParams p, const __grid_constant__ CUtens
           noise = (cf.sqrt_recip_acp * xt - x0v) / cf.sqrt_recipm1_acp;
         }
         float xn = cf.sqrt_acp_prev * x0v + cf.dir_coef * noise;
-        if (p.z) xn += cf.noise_coef * p.z[idx];
+        if (p.z) xn += cf.noise_coef * final_noise(p)[idx];
         p.x[idx] = xn;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // Y consumed before the next tile overwrites it

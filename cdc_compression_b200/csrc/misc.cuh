@@ -254,7 +254,14 @@ struct FinalParams {
   const cdc_step_coef* table;
   const int* step_ptr;
   int variant, pred_mode, clip_mode;
+  // eta != 0 inside the captured loop: z holds the noise of several consecutive steps, step i at z + (*z_first - i) * z_stride
+  const int* z_first;   // null: z is this step's tensor
+  long long z_stride;
 };
+
+__device__ __forceinline__ const float* final_noise(const FinalParams& p) {
+  return p.z_first ? p.z + (long long)(*p.z_first - *p.step_ptr) * p.z_stride : p.z;
+}
 
 constexpr int kFinalWStride = 49 * 64 + 8;
 constexpr int kFinalHalo = 22;
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(256) final_conv_kernel(const FinalParams p) {
           noise = (cf.sqrt_recip_acp * xt - x0v) / cf.sqrt_recipm1_acp;
         }
         float xn = cf.sqrt_acp_prev * x0v + cf.dir_coef * noise;
-        if (p.z) xn += cf.noise_coef * p.z[idx];
+        if (p.z) xn += cf.noise_coef * final_noise(p)[idx];
         p.x[idx] = xn;
       }
 }
@@ -600,7 +607,7 @@ __global__ void __launch_bounds__(256) final_conv_kx_kernel(const FinalParams p)
       noise = (cf.sqrt_recip_acp * xt - x0v) / cf.sqrt_recipm1_acp;
     }
     float xn = cf.sqrt_acp_prev * x0v + cf.dir_coef * noise;
-    if (p.z) xn += cf.noise_coef * p.z[idx];
+    if (p.z) xn += cf.noise_coef * final_noise(p)[idx];
     p.x[idx] = xn;
   }
 }

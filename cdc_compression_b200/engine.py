@@ -262,6 +262,21 @@ class DenoiserEngine:
                                             W, _ptr(ws), ws.numel(), self._stream()), "cdc_ddim_step")
         return x
 
+    def sample_loop_noise(self, x: torch.Tensor, i_first: int, i_last: int, z: torch.Tensor, pred_mode: str,
+                          clip_mode: str):
+        """In-place DDIM loop with eta != 0 over schedule indices i_first..i_last; ``z[j]`` is the standard-normal tensor of
+        step i_first - j (drawn by the caller in loop order).  One CUDA-graph replay per step."""
+        B, H, W = self._prep_x(x)
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        n = i_first - i_last + 1
+        if z.device != self.device or z.dtype != torch.float32 or not z.is_contiguous() or z.numel() < n * x.numel():
+            raise EngineError("noise buffer must be a contiguous fp32 CUDA tensor holding one x-shaped tensor per step")
+        ws = self._workspace(B, H, W)
+        self._check(self._lib.cdc_sample_loop_noise(self._h, _ptr(x), int(i_first), int(i_last), _ptr(z), PRED[pred_mode],
+                                                    CLIP[clip_mode], B, H, W, _ptr(ws), ws.numel(), self._stream()),
+                    "cdc_sample_loop_noise")
+        return x
+
     def sample_loop(self, x: torch.Tensor, i_first: int, i_last: int, pred_mode: str, clip_mode: str):
         """In-place eta=0 DDIM loop over schedule indices i_first..i_last (CUDA-graph replay per step)."""
         B, H, W = self._prep_x(x)

@@ -7,7 +7,7 @@
  * upstream tree).  Plain pointers and sizes only — no torch types.  All device pointers are
  * owned by the caller (PyTorch allocates inputs, outputs and the workspace); the engine owns
  * only the repacked weights.  The compute entry points (cdc_unet_forward, cdc_set_context,
- * cdc_set_schedule, cdc_context_decode, cdc_ddim_step, cdc_sample_loop) enqueue their work on the
+ * cdc_set_schedule, cdc_context_decode, cdc_ddim_step, cdc_sample_loop, cdc_sample_loop_noise) enqueue their work on the
  * caller's stream and never synchronise it (cdc_set_schedule stages the table in an engine-owned
  * pinned buffer and waits only for its OWN previous copy, if that is still in flight; growing the
  * table re-allocates it); the introspection entry points marked "(synchronises)" do.  Every entry
@@ -137,6 +137,14 @@ int cdc_ddim_step(cdc_engine* e, float* x_inout, int i, const float* z, int pred
 int cdc_sample_loop(cdc_engine* e, float* x_inout, int i_first, int i_last, int pred_mode,
                     int clip_mode, int B, int H, int W, void* workspace, int64_t workspace_bytes,
                     void* stream);
+
+/* ---- the same loop for eta != 0 (the reference adds eta * sigma_t * randn_like(x) every step, denoising_diffusion.py:150;
+ * xparam :171): z holds the standard-normal tensors of the (i_first - i_last + 1) steps of this call back to back, step i
+ * at z + (i_first - i) * B*channels*H*W (the caller draws them with PyTorch's generator, in loop order, so the random
+ * stream is the reference's).  One graph replay per step; the graph is re-captured when z changes. */
+int cdc_sample_loop_noise(cdc_engine* e, float* x_inout, int i_first, int i_last, const float* z,
+                          int pred_mode, int clip_mode, int B, int H, int W, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 
 /* ---- introspection (tests, bench) ---- */
 /* number of kernel launches one U-Net forward / one DDIM step enqueues for this shape */

@@ -327,3 +327,35 @@ def test_compress_with_engine_context_decoder_matches_pytorch_decoder(variant):
     psnr = O.batch_psnr(to01(outs["1"][0]), to01(outs["0"][0])).min().item()
     print(f"\n[parity] compress {variant}: engine vs PyTorch context decoder PSNR {psnr:.1f} dB")
     assert psnr > 50.0, psnr
+
+
+@pytest.mark.parametrize("variant", ["eps", "x"])
+def test_eta_nonzero_loop_runs_as_graph_chunks_with_the_reference_random_stream(variant, monkeypatch):
+    """eta != 0: the noise of a chunk of steps is drawn up front (one generator call per step, in loop order) and the chunk
+    runs as CUDA-graph replays (cdc_sample_loop_noise).  Must equal, bit for bit, the per-step path — engine.ddim_step fed
+    with randn_like drawn step by step from the same seed, which is how the reference consumes its generator
+    (denoising_diffusion.py:150) — and leave the generator in the same state."""
+    monkeypatch.setenv("CDC_NOISE_STEPS", "3")           # 7 steps = chunks of 3 + 3 + 1
+    B, H, W, seed, S, eta = 2, 32, 32, 0, 7, 0.7
+    d = unet_on_gpu(variant, seed)
+    _, _, ctx, init = case_inputs(variant, B, H, W, seed)
+    ctxd = [c.to(dev()) for c in ctx]
+    d.set_sample_schedule(S, dev())
+    torch.cuda.manual_seed(77)
+    if variant == "eps":
+        out = d.p_sample_loop(init.shape, ctxd, "ddim", init=init.to(dev()), eta=eta)
+        pred, clip = "noise", "none"
+    else:
+        out = d.p_sample_loop(init.shape, ctxd, clip_denoised=True, init=init.to(dev()), eta=eta)
+        pred, clip = "x", "full"
+    after = torch.randn(4, device=dev())
+    # per-step reference path on the same engine
+    torch.cuda.manual_seed(77)
+    x = init.clone().to(dev()).contiguous()
+    eng = d._bind(x, ctxd, eta)
+    eng.set_context(ctxd, B, H, W)
+    for i in reversed(range(S)):
+        eng.ddim_step(x, i, torch.randn_like(x), pred, clip)
+    assert torch.equal(out, x), (out - x).abs().max()
+    assert torch.equal(after, torch.randn(4, device=dev()))
+    assert torch.isfinite(out).all()
