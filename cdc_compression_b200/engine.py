@@ -32,6 +32,21 @@ def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+class _nvtx:
+    """NVTX range around one engine call (the build owns the tracing hooks): `ncu --nvtx --nvtx-include
+    "cdc.sample_loop/"` or a timeline tool can then pick out the phases of a decode.  Costs ~100 ns per call."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 class DenoiserEngine:
     """One engine per (device, Unet instance).  ``device=None`` builds a planning-only engine
     (workspace sizes, launch counts, FLOPs, weight validation) that cannot compute."""
@@ -209,15 +224,17 @@ class DenoiserEngine:
         ws = self._workspace(B, H, W)
         arr, keep = self._ctx_array(context, B, H, W)
         out = torch.empty_like(xin)
-        self._check(self._lib.cdc_unet_forward(self._h, _ptr(xin), _ptr(t), arr, len(keep), _ptr(out), B, H, W,
-                                               _ptr(ws), ws.numel(), self._stream()), "cdc_unet_forward")
+        with _nvtx("cdc.unet_forward"):
+            self._check(self._lib.cdc_unet_forward(self._h, _ptr(xin), _ptr(t), arr, len(keep), _ptr(out), B, H, W,
+                                                   _ptr(ws), ws.numel(), self._stream()), "cdc_unet_forward")
         return out
 
     def set_context(self, context: Sequence[torch.Tensor], B, H, W):
         ws = self._workspace(B, H, W)
         arr, keep = self._ctx_array(context, B, H, W)
-        self._check(self._lib.cdc_set_context(self._h, arr, len(keep), B, H, W, _ptr(ws), ws.numel(),
-                                              self._stream()), "cdc_set_context")
+        with _nvtx("cdc.set_context"):
+            self._check(self._lib.cdc_set_context(self._h, arr, len(keep), B, H, W, _ptr(ws), ws.numel(),
+                                                  self._stream()), "cdc_set_context")
 
     def has_context_decoder(self) -> bool:
         return self._check(self._lib.cdc_engine_has_context_decoder(self._h), "cdc_engine_has_context_decoder") == 1
@@ -231,8 +248,9 @@ class DenoiserEngine:
         if q.dim() != 4 or q.shape[0] != B or q.shape[2] * 16 != H or q.shape[3] * 16 != W:
             raise EngineError(f"latent has shape {tuple(q.shape)}; expected [B={B}, C, {H // 16}, {W // 16}]")
         ws = self._workspace(B, H, W)
-        self._check(self._lib.cdc_context_decode(self._h, _ptr(q), B, H, W, _ptr(ws), ws.numel(), self._stream()),
-                    "cdc_context_decode")
+        with _nvtx("cdc.context_decode"):
+            self._check(self._lib.cdc_context_decode(self._h, _ptr(q), B, H, W, _ptr(ws), ws.numel(), self._stream()),
+                        "cdc_context_decode")
 
     def read_context(self, level: int, B, H, W) -> torch.Tensor:
         """Context map ``level`` as the engine holds it, as fp32 NCHW (tests)."""
@@ -258,8 +276,9 @@ class DenoiserEngine:
         ws = self._workspace(B, H, W)
         if z is not None:
             z = z.to(torch.float32).contiguous()
-        self._check(self._lib.cdc_ddim_step(self._h, _ptr(x), int(i), _ptr(z), PRED[pred_mode], CLIP[clip_mode], B, H,
-                                            W, _ptr(ws), ws.numel(), self._stream()), "cdc_ddim_step")
+        with _nvtx("cdc.ddim_step"):
+            self._check(self._lib.cdc_ddim_step(self._h, _ptr(x), int(i), _ptr(z), PRED[pred_mode], CLIP[clip_mode], B, H,
+                                                W, _ptr(ws), ws.numel(), self._stream()), "cdc_ddim_step")
         return x
 
     def sample_loop_noise(self, x: torch.Tensor, i_first: int, i_last: int, z: torch.Tensor, pred_mode: str,
@@ -272,9 +291,10 @@ class DenoiserEngine:
         if z.device != self.device or z.dtype != torch.float32 or not z.is_contiguous() or z.numel() < n * x.numel():
             raise EngineError("noise buffer must be a contiguous fp32 CUDA tensor holding one x-shaped tensor per step")
         ws = self._workspace(B, H, W)
-        self._check(self._lib.cdc_sample_loop_noise(self._h, _ptr(x), int(i_first), int(i_last), _ptr(z), PRED[pred_mode],
-                                                    CLIP[clip_mode], B, H, W, _ptr(ws), ws.numel(), self._stream()),
-                    "cdc_sample_loop_noise")
+        with _nvtx("cdc.sample_loop_noise"):
+            self._check(self._lib.cdc_sample_loop_noise(self._h, _ptr(x), int(i_first), int(i_last), _ptr(z), PRED[pred_mode],
+                                                        CLIP[clip_mode], B, H, W, _ptr(ws), ws.numel(), self._stream()),
+                        "cdc_sample_loop_noise")
         return x
 
     def sample_loop(self, x: torch.Tensor, i_first: int, i_last: int, pred_mode: str, clip_mode: str):
@@ -282,7 +302,8 @@ class DenoiserEngine:
         B, H, W = self._prep_x(x)
         assert x.dtype == torch.float32 and x.is_contiguous()
         ws = self._workspace(B, H, W)
-        self._check(self._lib.cdc_sample_loop(self._h, _ptr(x), int(i_first), int(i_last), PRED[pred_mode],
-                                              CLIP[clip_mode], B, H, W, _ptr(ws), ws.numel(), self._stream()),
-                    "cdc_sample_loop")
+        with _nvtx("cdc.sample_loop"):
+            self._check(self._lib.cdc_sample_loop(self._h, _ptr(x), int(i_first), int(i_last), PRED[pred_mode],
+                                                  CLIP[clip_mode], B, H, W, _ptr(ws), ws.numel(), self._stream()),
+                        "cdc_sample_loop")
         return x
