@@ -674,40 +674,59 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
       const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB;
       const int dyp = p.phases > 1 ? (ph >> 1) - 1 : 0, dxp = p.phases > 1 ? (ph & 1) - 1 : 0;
       const int wsel = p.phases > 1 ? ph : (p.w_rows_per_image ? b0 : 0);   // weight set: phase | image
-      int sc = 0;
+      // Only the unit's own K range [sc0, sc1) is visited: a K-split unit used to walk (and skip) every super-chunk before
+      // and after its range — ~220 cycles per skipped iteration (divergence bookkeeping), up to 10 k cycles before the
+      // first load of the units with the highest K-split index (measured with per-stage timestamps, round 2).
+      int seg_base = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const TcSeg sg = p.seg[s];
         const CUtensorMap* mA = &maps.a[s];
         const CUtensorMap* mB = &maps.b[s];
         const uint32_t tx_bytes = (uint32_t)(sg.a_bytes + sg.nw * N * 128);
-        for (int kyo = 0; kyo < sg.kh; kyo += sg.vr)
-          for (int kx = 0; kx < sg.kw; ++kx)
-            for (int cc = 0; cc < sg.cpt; ++cc, ++sc) {
-              if (sc < sc0 || sc >= sc1) continue;
-              const long long w0 = CDC_CLK();
-              tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              c_wait += CDC_CLK() - w0;
-              ++c_n;
-              if (leader) {
-                const uint32_t sA = base + stage * stage_bytes;
-                const uint32_t sB = sA + p.b_off;
-                const uint32_t full = bar_full + 8 * stage;
-                tc::mbar_expect_tx(full, tx_bytes);
-                // one activation box: TH + vr - 1 tile rows starting at the first vertical tap
-                tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp,
-                                y0 * p.stride + kyo + sg.dy0 + dyp, b0);
-                // the weight tiles of the vr vertical taps it feeds: [piece][tap][n_piece rows]
-                for (int pc = 0; pc < p.n_split; ++pc)
-                  tc::tma_load_4d(sB + pc * sg.nw * p.n_piece * 128, mB, full, 0,
-                                  (kx * sg.cpt + cc) * p.Ntot + slice * N + pc * p.n_piece, kyo,
-                                  (sg.wshared || sg.dual) ? 0 : wsel);
-              }
-              __syncwarp();
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
-              }
+        const int per_ky = sg.kw * sg.cpt;
+        const int nsc_s = (sg.kh / sg.vr) * per_ky;
+        const int lo = max(sc0 - seg_base, 0), hi = min(sc1 - seg_base, nsc_s);
+        seg_base += nsc_s;
+        if (lo >= hi) continue;
+        int kyo = 0, kx = 0, cc = 0;
+        if (lo > 0) {   // K split: first super-chunk of the range inside this segment
+          const int kyi = lo / per_ky, r2 = lo - kyi * per_ky;
+          kyo = kyi * sg.vr;
+          kx = r2 / sg.cpt;
+          cc = r2 - kx * sg.cpt;
+        }
+        for (int j = lo; j < hi; ++j) {
+          const long long w0 = CDC_CLK();
+          tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          c_wait += CDC_CLK() - w0;
+          ++c_n;
+          if (leader) {
+            const uint32_t sA = base + stage * stage_bytes;
+            const uint32_t sB = sA + p.b_off;
+            const uint32_t full = bar_full + 8 * stage;
+            tc::mbar_expect_tx(full, tx_bytes);
+            // one activation box: TH + vr - 1 tile rows starting at the first vertical tap
+            tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp,
+                            y0 * p.stride + kyo + sg.dy0 + dyp, b0);
+            // the weight tiles of the vr vertical taps it feeds: [piece][tap][n_piece rows]
+            for (int pc = 0; pc < p.n_split; ++pc)
+              tc::tma_load_4d(sB + pc * sg.nw * p.n_piece * 128, mB, full, 0,
+                              (kx * sg.cpt + cc) * p.Ntot + slice * N + pc * p.n_piece, kyo,
+                              (sg.wshared || sg.dual) ? 0 : wsel);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++cc == sg.cpt) {
+            cc = 0;
+            if (++kx == sg.kw) {
+              kx = 0;
+              kyo += sg.vr;
             }
+          }
+        }
       }
     }
     if (clk && leader) {
@@ -740,7 +759,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
       tc::tc_fence_after();
       const uint32_t d_tmem0 = tmem_base + (uint32_t)(buf * Nacc);
       uint32_t acc_started = 0;   // bit a: accumulator a already holds a partial sum of this tile
-      int sc = 0;
+      int seg_base = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const int vr = p.seg[s].vr;
         const int nw = p.seg[s].nw;
@@ -748,8 +767,9 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
         const int sacc = p.seg[s].acc;
         const uint32_t d_tmem = d_tmem0 + (uint32_t)(sacc * N);
         const int nsc = (p.seg[s].kh / vr) * p.seg[s].kw * p.seg[s].cpt;
-        for (int i = 0; i < nsc; ++i, ++sc) {
-          if (sc < sc0 || sc >= sc1) continue;
+        const int lo = max(sc0 - seg_base, 0), hi = min(sc1 - seg_base, nsc);   // the unit's K range inside this segment
+        seg_base += nsc;
+        for (int i = lo; i < hi; ++i) {
           const long long w1 = CDC_CLK();
           tc::mbar_wait(bar_full + 8 * stage, phase);
           c_wf += CDC_CLK() - w1;
