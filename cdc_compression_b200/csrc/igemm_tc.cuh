@@ -203,6 +203,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Predicated forms (issue iff pred != 0): the elected lane issues without a divergent branch — no BSSY / BSYNC / WARPSYNC
+// bookkeeping per pipeline stage in the producer and MMA loops, which are single-warp latency chains.
+__device__ __forceinline__ void mbar_expect_tx_if(uint32_t pred, uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %2;\n\t}"
+      ::"r"(pred), "r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_if(uint32_t pred, uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2, {%4, %5, %6, %7}], [%3];\n\t}"
+      ::"r"(pred), "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -240,6 +257,25 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint
       "setp.ne.b32 p, %5, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_lo_if(uint32_t pred, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t pred, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
+      ::"r"(pred), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -657,6 +693,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
     // The whole warp walks the loop converged (uniform control flow keeps the index math in uniform registers);
     // one elected lane issues the copies.
     const bool leader = tc::elect_one();
+    const uint32_t lead = leader ? 1u : 0u;
     int stage = 0;
     uint32_t phase = 0;
     long long c_wait = 0, c_n = 0;
@@ -700,21 +737,20 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
           tc::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           c_wait += CDC_CLK() - w0;
           ++c_n;
-          if (leader) {
+          {
             const uint32_t sA = base + stage * stage_bytes;
             const uint32_t sB = sA + p.b_off;
             const uint32_t full = bar_full + 8 * stage;
-            tc::mbar_expect_tx(full, tx_bytes);
+            tc::mbar_expect_tx_if(lead, full, tx_bytes);
             // one activation box: TH + vr - 1 tile rows starting at the first vertical tap
-            tc::tma_load_4d(sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp,
-                            y0 * p.stride + kyo + sg.dy0 + dyp, b0);
+            tc::tma_load_4d_if(lead, sA, mA, full, cc * 64, x0 * p.stride + kx + sg.dx0 + dxp,
+                               y0 * p.stride + kyo + sg.dy0 + dyp, b0);
             // the weight tiles of the vr vertical taps it feeds: [piece][tap][n_piece rows]
             for (int pc = 0; pc < p.n_split; ++pc)
-              tc::tma_load_4d(sB + pc * sg.nw * p.n_piece * 128, mB, full, 0,
-                              (kx * sg.cpt + cc) * p.Ntot + slice * N + pc * p.n_piece, kyo,
-                              (sg.wshared || sg.dual) ? 0 : wsel);
+              tc::tma_load_4d_if(lead, sB + pc * sg.nw * p.n_piece * 128, mB, full, 0,
+                                 (kx * sg.cpt + cc) * p.Ntot + slice * N + pc * p.n_piece, kyo,
+                                 (sg.wshared || sg.dual) ? 0 : wsel);
           }
-          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -740,6 +776,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
     // Whole warp converged, one elected lane issues (the same lane every time: tcgen05.commit tracks the MMAs of
     // the thread that executes it).
     const bool leader = tc::elect_one();
+    const uint32_t lead = leader ? 1u : 0u;
     const uint32_t idesc = tc::make_idesc_f16(p.n_piece);
     const uint32_t desc_hi = (uint32_t)(tc::make_desc_sw128(0) >> 32);
     const uint32_t b_step = (uint32_t)(p.n_piece * 128) >> 4;    // one weight tile
@@ -775,7 +812,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
           c_wf += CDC_CLK() - w1;
           tc::tc_fence_after();
           const uint32_t accumulate = (acc_started >> sacc) & 1u;
-          if (leader) {
+          {
             const uint32_t a_lo = (uint32_t)tc::make_desc_sw128(base + stage * stage_bytes);
             const uint32_t b_lo = a_lo + ((uint32_t)p.b_off >> 4);
             if (p.n_split == 1) {
@@ -785,21 +822,20 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
                 const uint32_t av = a_lo + v * avs, bv = b_lo + v * b_step;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  tc::umma_f16_lo(d_tmem, av + ks * 2, bv + ks * 2, desc_hi, idesc,
-                                  (ks == 0 && v == 0) ? accumulate : 1u);
+                  tc::umma_f16_lo_if(lead, d_tmem, av + ks * 2, bv + ks * 2, desc_hi, idesc,
+                                     (ks == 0 && v == 0) ? accumulate : 1u);
               }
             } else {
               for (int v = 0; v < nw; ++v)
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   for (int pc = 0; pc < p.n_split; ++pc)
-                    tc::umma_f16_lo(d_tmem + pc * p.n_piece, a_lo + v * avs + ks * 2,
-                                    b_lo + (pc * nw + v) * b_step + ks * 2, desc_hi, idesc,
-                                    (ks == 0 && v == 0) ? accumulate : 1u);
+                    tc::umma_f16_lo_if(lead, d_tmem + pc * p.n_piece, a_lo + v * avs + ks * 2,
+                                       b_lo + (pc * nw + v) * b_step + ks * 2, desc_hi, idesc,
+                                       (ks == 0 && v == 0) ? accumulate : 1u);
             }
-            tc::umma_commit(bar_empty + 8 * stage);  // frees this smem stage once the MMAs above retire
+            tc::umma_commit_if(lead, bar_empty + 8 * stage);  // frees this smem stage once the MMAs above retire
           }
-          __syncwarp();
           acc_started |= 1u << sacc;
           if (++stage == p.stages) {
             stage = 0;
@@ -807,8 +843,7 @@ igemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvParams p,
           }
         }
       }
-      if (leader) tc::umma_commit(bar_tfull + 8 * buf);  // accumulator of this tile complete
-      __syncwarp();
+      tc::umma_commit_if(lead, bar_tfull + 8 * buf);  // accumulator of this tile complete
     }
     if (clk && leader) {
       p.dbg_clk[3] += CDC_CLK() - c_t0;
