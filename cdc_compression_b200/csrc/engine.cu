@@ -174,6 +174,7 @@ struct Act {  // fp16 NHWC activation in the workspace (+ optional compensation 
   size_t off = 0, bytes = 0;
   size_t off_lo = 0;  // 0 = none.  value = hi + lo, lo = fp16(value - hi): kept for the "trunk" activations
   int C = 0, H = 0, W = 0;
+  bool win8 = false;   // packed network input in window form (ConvSeg::win8)
 };
 
 struct Plan {
@@ -801,6 +802,7 @@ struct Builder {
       p.seg[i].dy0 = segs[i].dy0;
       p.seg[i].dx0 = segs[i].dx0;
       p.seg[i].nchunk = segs[i].kh * segs[i].kw * (segs[i].a.C / 64);
+      p.seg[i].win8 = segs[i].a.win8 ? 1 : 0;
       total += p.seg[i].nchunk;
     }
     p.Hs = segs[0].a.H;
@@ -1214,14 +1216,21 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op, bool allow_dual = true) {
     dropped[i] = false;
     dual_with[i] = -1;
   }
-  if (dual_ok)
+  // 1 x 1 segment pairs (the W_hi / W_lo passes of a fused res_conv) may share their activation load inside a vertical-reuse
+  // launch too: a stage then carries two weight tiles and no tap offset, next to the convolution's kh-tile stages
+  const bool dual_1x1 = allow_dual && e->dual_pass && c.groups == 1 && !c.phases && c.stride == 1;
+  if (dual_ok || dual_1x1)
     for (int i = 0; i < c.nseg; ++i) {
-      if (dropped[i] || dual_with[i] >= 0 || c.seg[i].W) continue;
+      if (dropped[i] || dual_with[i] >= 0) continue;
       for (int j = i + 1; j < c.nseg; ++j) {
         const ConvSeg &a = c.seg[i], &b2 = c.seg[j];
-        if (dropped[j] || b2.W || a.src != b2.src || a.C != b2.C || a.kh != b2.kh || a.kw != b2.kw || a.dy0 != b2.dy0 ||
+        if (dropped[j] || a.src != b2.src || a.C != b2.C || a.kh != b2.kh || a.kw != b2.kw || a.dy0 != b2.dy0 ||
             a.dx0 != b2.dx0 || a.acc != b2.acc)
           continue;
+        if (!dual_ok && !(a.kh == 1 && a.kw == 1)) continue;
+        // segments with their own weight pointer: the W_lo set must sit where the chunk numbering says (same blob, same order)
+        if ((a.W == nullptr) != (b2.W == nullptr)) continue;
+        if (a.W && (b2.W - a.W) != (long long)(cq0[j] - cq0[i]) * N * 64) continue;
         dual_with[i] = j;
         dropped[j] = true;
         break;
@@ -1328,7 +1337,15 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op, bool allow_dual = true) {
       t.b_off = b_off;
       t.vr_max = khmax;
       t.total_sc = 0;
-      for (int i = 0; i < t.nseg; ++i) {   // (no dual segments in this mode: dual_ok excludes it)
+      for (int i = 0; i < t.nseg; ++i) {
+        if (t.seg[i].dual) {   // 1 x 1 dual segment: one box of the tile's own rows, two weight tiles, no tap offset
+          t.seg[i].vr = 1;
+          t.seg[i].nw = 2;
+          t.seg[i].avstep = 0;
+          t.seg[i].a_bytes = 128 * t.TW * t.TH;
+          t.total_sc += t.seg[i].kw * t.seg[i].cpt;
+          continue;
+        }
         t.seg[i].vr = t.seg[i].kh;
         t.seg[i].nw = t.seg[i].kh;
         t.seg[i].avstep = (t.TW * 128) >> 4;
@@ -1400,6 +1417,11 @@ int setup_tc(cdc_engine* e, Plan* pl, Op& op, bool allow_dual = true) {
     const cuuint64_t ws_ = (cuuint64_t)c.Ws, hs_ = (cuuint64_t)c.Hs;
     cuuint64_t gdim[4] = {Cs, ws_, hs_, (cuuint64_t)B};
     cuuint64_t gstr[3] = {Cs * 2, ws_ * Cs * 2, hs_ * ws_ * Cs * 2};
+    if (cs.win8) {   // overlapping windows: pixel stride 16 B under a 128-B inner extent (tests/microbench/tma_window.cu)
+      gstr[0] = 16;
+      gstr[1] = (ws_ + 8) * 16;
+      gstr[2] = hs_ * (ws_ + 8) * 16;
+    }
     // strided convolution: the box spans stride*T source pixels, of which every stride-th is loaded (a dense 5-D
     // parity view of the source was measured: no faster)
     const cuuint32_t sx = (cuuint32_t)c.stride;
@@ -1569,14 +1591,15 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
     pl->time_op = (int)pl->ops.size() - 1;
     bd.pending_time_join = op.lane == 1;
   }
-  Act x0 = bd.new_act(64, H, W);
+  Act x0 = bd.new_act(64, H, W);   // window form [B][H][W + 8][8] (1/8 of the allocation is used)
+  x0.win8 = true;
   {
     pl->ops.emplace_back();
     Op& op = pl->ops.back();
     op.kind = OP_PACK;
     op.name = "pack_input";
-    op.dbg = bd.ws<__half>(x0.off);
-    op.dC = 64; op.dH = H; op.dW = W;
+    op.dbg = nullptr;   // window form: no [B][H][W][64] view to read back
+    op.lat.hi = bd.ws<__half>(x0.off);
     pl->pack_op = (int)pl->ops.size() - 1;
   }
   auto ctx_act = [&](int l) {
@@ -1605,7 +1628,7 @@ int build_plan(cdc_engine* e, Plan* pl, int B, int H, int W, uint8_t* wsp) {
       s1.push_back({x, 3, 1, -3, 0});
       s1.push_back({x, 2, 1, 0, 0});
       s1.push_back({x, 2, 1, 2, 0});
-      sr.push_back({x, 1, 1, 0, 0, false, true});
+      sr.push_back({x, 1, 1, 0, 0});   // (hi weights, then the weight remainder as its own K chunk: window form has no spare centre copy)
       if (has_ctx && !e->fold_ctx0) {
         s1.push_back({ctx_act(0), 3, 7, -3, -3});
         s1.push_back({ctx_act(0), 2, 7, 0, -3});
@@ -1870,12 +1893,12 @@ int run_op(cdc_engine* e, Plan* pl, const Op& op, size_t i, const RunArgs& a, cu
         break;
       }
       case OP_PACK: {
-        const long long total = (long long)B * H * W * 8;
+        const long long total = (long long)B * H * (W + 8);
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 64);
         const float* c0 = e->fold_ctx0 ? reinterpret_cast<const float*>(pl->ws + pl->ctx_off[0]) : nullptr;
         launch_k(pack_input_kernel, dim3(blocks), dim3(256), 0, st, a.x, (int)cfg.channels, c0,
-                 (int)(e->fold_ctx0 ? cfg.context_channels : 0), B, H, W, make_fastdiv((uint32_t)W),
-                 make_fastdiv((uint32_t)H), const_cast<__half*>(op.dbg));
+                 (int)(e->fold_ctx0 ? cfg.context_channels : 0), B, H, W, make_fastdiv((uint32_t)(W + 8)),
+                 make_fastdiv((uint32_t)H), op.lat.hi);
         break;
       }
       case OP_CONV: {
@@ -2215,7 +2238,7 @@ int cdc_engine_finalize(cdc_engine* e) {
     if (l == 0) {
       const int folded = (has_ctx && e->fold_ctx0) ? cc : 0;
       s1.push_back({64, 7, 1, 1, 0, cx + folded});
-      sr.push_back({64, 1, 1, 3, 0, cx + folded});
+      sr.push_back({64, 1, 1, 2, 0, cx + folded});
       if (has_ctx && !e->fold_ctx0) {
         s1.push_back({cc, 7, 7, 0, cx, 0});
         sr.push_back({cc, 1, 1, 0, cx, 0});

@@ -30,6 +30,10 @@ struct ConvSeg {
   int acc;
   const __half* W;
   int wshared;        // with per-image weights (groups > 1): this segment's weights are shared by all images
+  // packed network input in window form: src is [B][Hs][Ws + 8][8] fp16 (3 zero pixels left, 5 right) and "channel" k of
+  // pixel x is element k of the 64 halves starting at pixel x (k = kx * 8 + c: the horizontal taps x + kx - 3 of the 7 x 7
+  // convolution) — an overlapping-window view, 8x smaller than the materialised [B][Hs][Ws][64] tensor
+  int win8;
 };
 
 struct ConvParams {
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(256) igemm_hmma_kernel(const ConvParams p) {
   const int HoWo = p.Ho * p.Wo;
 
   // ---- per-thread A-row bookkeeping (fixed across the K loop) ----
-  int a_iy[AR], a_ix[AR], a_pix[AR];
+  int a_iy[AR], a_ix[AR], a_pix[AR], a_b[AR];
   const int a_chunk = tid & 7;
 #pragma unroll
   for (int i = 0; i < AR; ++i) {
@@ -167,10 +171,12 @@ __global__ void __launch_bounds__(256) igemm_hmma_kernel(const ConvParams p) {
       a_iy[i] = oy * p.stride + dyp;
       a_ix[i] = ox * p.stride + dxp;
       a_pix[i] = b * p.Hs * p.Ws;
+      a_b[i] = b;
     } else {
       a_iy[i] = -(1 << 28);
       a_ix[i] = -(1 << 28);
       a_pix[i] = 0;
+      a_b[i] = 0;
     }
   }
 
@@ -195,7 +201,10 @@ __global__ void __launch_bounds__(256) igemm_hmma_kernel(const ConvParams p) {
       const int iy = a_iy[i] + dy, ix = a_ix[i] + dx;
       const bool ok = (unsigned)iy < (unsigned)p.Hs && (unsigned)ix < (unsigned)p.Ws;
       const __half* src = sg.src;
-      if (ok) src += (size_t)(a_pix[i] + iy * p.Ws + ix) * sg.C + cc * 64 + a_chunk * 8;
+      if (ok) {
+        if (sg.win8) src += ((size_t)(a_b[i] * p.Hs + iy) * (p.Ws + 8) + ix) * 8 + a_chunk * 8;
+        else src += (size_t)(a_pix[i] + iy * p.Ws + ix) * sg.C + cc * 64 + a_chunk * 8;
+      }
       cp_async16(sA + swz128(row, a_chunk), src, ok ? 16 : 0);
     }
     const __half* wsrc = W + ((size_t)q * p.Ntot + n0) * 64 + a_chunk * 8;

@@ -14,23 +14,24 @@ namespace cdc {
 //   remainders there, the 7x7 conv has zero weights for it.  Channels >= cx+cc of every slot are zero.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_input_kernel(const float* __restrict__ x, int cx, const float* __restrict__ ctx, int cc,
-                                  int B, int H, int W, FastDiv fdW, FastDiv fdH, __half* __restrict__ out) {
+                                  int B, int H, int W, FastDiv fdWp, FastDiv fdH, __half* __restrict__ out) {
+  // out: [B][H][W + 8][8] fp16 — pixel record = (x channels | folded context channels | zeros); 3 zero pixels on the left
+  // and 5 on the right of every row, so that the 64 halves starting at padded pixel x are the horizontal taps x-3 .. x+4 of
+  // logical pixel x (ConvSeg::win8: the convolution reads them through an overlapping-window tensor map)
   pdl_launch_dependents();
   pdl_wait();
-  const int total = B * H * W * 8;   // < 2^31 for every supported shape (checked by the engine)
+  const int Wp = W + 8;
+  const int total = B * H * Wp;   // < 2^31 for every supported shape (checked by the engine)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int kx = i & 7;
-    const int pix = i >> 3;
-    const int t = fdiv(pix, fdW);
-    const int xx = pix - t * W;
+    const int t = fdiv(i, fdWp);
+    const int xx = i - t * Wp - 3;
     const int b = fdiv(t, fdH);
     const int yy = t - b * H;
-    const int sx = kx < 7 ? xx + kx - 3 : xx;   // slot 7 repeats the centre pixel (weight-remainder pass of res_conv)
     float v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = 0.f;
-    if (sx >= 0 && sx < W) {
-      const size_t row = (size_t)yy * W + sx;
+    if (xx >= 0 && xx < W) {
+      const size_t row = (size_t)yy * W + xx;
       const size_t plane = (size_t)H * W;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
