@@ -269,7 +269,9 @@ def memory_bound_rows(wl, prof, peaks):
                                 3 * a0, 6 * a0),
         "ups.4.2 attention": (["ups.4.2.ctx", "ups.4.2.combine", "ups.4.2.T", "ups.4.2.M", "ups.4.2.out"],
                               3 * a0 // 4, 6 * a0 // 4),
-        "pack_input": (["pack_input"], xs + a0, xs + a0),
+        # window form: reads x_t and the folded eps context (fp32), writes [B][H][W+8][8] fp16
+        "pack_input": (["pack_input"], (2 if wl.variant == "eps" else 1) * xs + B * H * (W + 8) * 16,
+                       (2 if wl.variant == "eps" else 1) * xs + B * H * (W + 8) * 16),
     }
     traffic = {}
     try:
