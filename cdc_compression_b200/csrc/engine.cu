@@ -364,8 +364,8 @@ struct SegSpec {  // how one K-segment of a conv maps onto the reference's OIHW 
   int mode;       // 0: channel k of chunk cc at tap (ty,tx) <- W[o][coff + cc*64+k][ty][tx]
                   // 1: packed input X0: k = kx*8 + c (c < creal) at vertical tap ty <- W[o][coff + c][ty][kx]  (kw==1)
                   // 2: packed input X0, 1x1 conv: k = 3*8 + c <- W[o][coff + c][0][0]
-                  // 3: like 2, plus the weight remainder fp16(w - fp16(w)) at k = 7*8 + c (X0 carries a second
-                  //    copy of the centre pixel there), so hi and lo weight passes share one K chunk
+                  // 3: (unused since the packed input is in window form, where slot 7 is pixel x+4 and not a second copy of
+                  //    the centre pixel) like 2, plus the weight remainder fp16(w - fp16(w)) at k = 7*8 + c
   int coff;       // first reference input channel of this segment
   int creal;      // real channels (mode 1/2)
   int part = 0;   // 0: fp16(w)   1: fp16(w - fp16(w))  (weight compensation term of the 3-pass trunk convolutions)

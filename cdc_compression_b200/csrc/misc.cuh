@@ -8,10 +8,11 @@ namespace cdc {
 
 // ------------------------------------------------------------------------------------------------
 // x_t (fp32 NCHW, `cx` channels) [+ a small fp32 NCHW context with `cc` channels, cx+cc <= 8]
-//   -> X0 [B,H,W,64] fp16 with channel kx*8+c = value at (y, x+kx-3): the horizontal taps of the first
-//   7x7 convolution (unet.py:61 / network_components.py:87) folded into K, so that conv runs as 7
-//   vertical taps of 64 channels.  Slot kx=7 repeats the centre pixel (kx=3): the 1x1 res_conv puts its fp16 weight
-//   remainders there, the 7x7 conv has zero weights for it.  Channels >= cx+cc of every slot are zero.
+//   -> the packed network input in WINDOW FORM, X8 [B][H][W+8][8] fp16: one 16-byte record per pixel (x channels | context
+//   channels | zeros), 3 zero pixels left and 5 right of every row.  The first 7x7 convolution (unet.py:61 /
+//   network_components.py:87) reads it through an overlapping-window tensor map (ConvSeg::win8): "channel" kx*8+c of pixel x
+//   = the value at (y, x+kx-3), i.e. the horizontal taps folded into K, so that the convolution runs as 7 vertical taps of 64
+//   channels.  Slot kx=7 (pixel x+4) has zero weights; the 1x1 res_conv reads slot kx=3 (the pixel itself).
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_input_kernel(const float* __restrict__ x, int cx, const float* __restrict__ ctx, int cc,
                                   int B, int H, int W, FastDiv fdWp, FastDiv fdH, __half* __restrict__ out) {
